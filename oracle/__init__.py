@@ -1,0 +1,7 @@
+"""ORACLE -- test infrastructure only (see hifigan_oracle.c / torch_port.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this package.  The product package never does.
+"""
+from .c_oracle import build_c_oracle, forward_c            # noqa: F401
+from .torch_port import forward_torch, fold_weight_norm    # noqa: F401
