@@ -1,0 +1,128 @@
+/*
+ * hfg.h -- C ABI of the B200-native HiFi-GAN generator inference path.
+ *
+ * This is the whole drop-in boundary: a plain-C shared library
+ * (libhfg_b200.so; no torch, no C++ types in any signature) that the host-side
+ * mirror of the reference's nn.Module binds with ctypes
+ * (tts-sambert_hifigan_b200/_capi.py).  The reference has no FFI of its own --
+ * its boundary is the Python class models/hifigan.py::HiFiGANGenerator used by
+ * composition (reference models/hifigan.py:681-689, called at :719) -- so each
+ * entry point below cites the reference method or attribute it stands behind.
+ *
+ * Conventions
+ *   - every function returns 0 (HFG_OK) or a negative hfg_status; nothing
+ *     throws across the ABI; hfg_last_error() gives the message of the last
+ *     failure on that handle;
+ *   - a handle belongs to the CUDA device that was current in hfg_create and is
+ *     not thread-safe (one handle per GPU, as one process drives one GPU);
+ *   - device pointers are plain CUDA device pointers owned by the caller
+ *     (PyTorch allocates them); `stream` is a cudaStream_t passed as void*;
+ *   - hfg_forward is asynchronous on `stream`.
+ *   - there is NO CPU fallback: without a CUDA device hfg_create fails with
+ *     HFG_ERR_CUDA.
+ */
+#ifndef HFG_H_
+#define HFG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFG_MAX_STAGES 8
+#define HFG_ABI_VERSION 1
+
+typedef struct hfg_handle hfg_handle;
+
+/* Constructor arguments of HiFiGANGenerator.__init__ (reference
+ * models/hifigan.py:149-158), flattened. */
+typedef struct hfg_config {
+    int32_t n_mels;                                   /* :151 */
+    int32_t num_upsamples;                            /* len(upsample_rates), :173 */
+    int32_t upsample_initial_channel;                 /* :154 */
+    int32_t num_resblocks;                            /* len(resblock_kernel_sizes), :172 */
+    int32_t upsample_rates[HFG_MAX_STAGES];           /* :152 */
+    int32_t upsample_kernel_sizes[HFG_MAX_STAGES];    /* :153 */
+    int32_t resblock_kernel_sizes[HFG_MAX_STAGES];    /* :155 */
+    int32_t num_dilations[HFG_MAX_STAGES];            /* len(resblock_dilation_sizes[j]) */
+    int32_t resblock_dilations[HFG_MAX_STAGES][HFG_MAX_STAGES]; /* :156 */
+} hfg_config;
+
+typedef enum hfg_status {
+    HFG_OK = 0,
+    HFG_ERR_INVALID = -1,     /* bad argument / shape mismatch (reference: ATen shape error) */
+    HFG_ERR_CUDA = -2,        /* CUDA runtime failure, or no CUDA device                     */
+    HFG_ERR_STATE = -3,       /* weights missing / not committed                             */
+    HFG_ERR_WORKSPACE = -4,   /* workspace too small or misaligned                           */
+    HFG_ERR_UNSUPPORTED = -5  /* mode not available for this configuration                   */
+} hfg_status;
+
+/* Arithmetic modes.  The output is always fp32 [B,1,T_out]
+ * (reference tests/test_hifigan_integration.py:50). */
+typedef enum hfg_mode {
+    HFG_MODE_FP32 = 0,  /* fp32 FFMA kernels, fp32 activations: strict parity mode      */
+    HFG_MODE_TF32 = 1,  /* tcgen05 kind::tf32, fp32 activations (parity <= 1e-3)          */
+    HFG_MODE_BF16 = 2   /* tcgen05 kind::f16 (bf16 operands), bf16 activations, fp32 acc  */
+} hfg_mode;
+
+int hfg_abi_version(void);
+
+/* HiFiGANGenerator.__init__ (reference models/hifigan.py:149-222). */
+int hfg_create(const hfg_config* cfg, hfg_handle** out);
+void hfg_destroy(hfg_handle* h);
+const char* hfg_last_error(const hfg_handle* h);
+
+/* One tensor of the module's state_dict, by its reference key
+ * ("conv_pre.weight", "ups.0.bias", "mrfs.1.resblocks.2.convs1.0.weight_g", ...;
+ * schema: SURVEY.md section 8b).  `data` is a HOST fp32 pointer in the
+ * reference's own layout ([C_out,C_in,k] for Conv1d, [C_in,C_out,k] for
+ * ConvTranspose1d); it is copied.  Replaces nn.Module.load_state_dict for this
+ * module.  Both the plain (.weight) and the weight-normed (.weight_g/.weight_v,
+ * reference models/hifigan.py:274-283) schema are accepted. */
+int hfg_set_weight(hfg_handle* h, const char* name, const float* data,
+                   const int64_t* shape, int32_t ndim);
+
+/* Fold weight-norm (w = g*v/||v||, norm over all dims but 0), repack every
+ * layer into kernel layout and upload.  Replaces remove_weight_norm()
+ * (reference models/hifigan.py:263-272).  Fails with HFG_ERR_STATE and names
+ * the first missing key if the state is incomplete. */
+int hfg_commit_weights(hfg_handle* h);
+
+/* T_out of forward() for Tfrm frames: each ConvTranspose1d maps
+ * T -> (T-1)*u - 2*((k-u)//2) + k (reference models/hifigan.py:196-202). */
+int hfg_out_len(const hfg_handle* h, int32_t frames, int64_t* out_len);
+
+int hfg_workspace_bytes(const hfg_handle* h, int32_t batch, int32_t frames, int32_t mode,
+                        size_t* bytes);
+
+/* HiFiGANGenerator.forward (reference models/hifigan.py:224-261):
+ * mel_dev fp32 [B, n_mels, Tfrm] contiguous  ->  wav_dev fp32 [B, 1, T_out]. */
+int hfg_forward(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames,
+                float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
+                void* stream);
+
+/* Same, and also copies the 2*num_upsamples+1 stage-boundary activations
+ * (conv_pre, then ups[i], mrfs[i] outputs; fp32 [B,C,T] device buffers; NULL
+ * entries are skipped) -- what forward hooks on the reference module observe.
+ * Test/debug entry point. */
+int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames,
+                       float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
+                       void* stream, float* const* stage_out_dev);
+
+/* End-to-end call with HOST buffers: stages mel through pinned memory, copies
+ * host->device, runs forward, copies the waveform back and synchronises.
+ * Pinned staging, workspace and stream are owned by the handle and grown on
+ * demand.  This is what `module(mel_cpu_tensor)` costs a caller whose data
+ * lives on the host. */
+int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
+                     float* wav_host, int32_t mode);
+
+/* Number of kernels the last hfg_forward* call on this handle launched. */
+int hfg_last_launch_count(const hfg_handle* h, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFG_H_ */

@@ -1,0 +1,76 @@
+"""The oracle (oracle/) against the committed golden vectors of the live
+reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import case_inputs, load_golden
+from tts_sambert_hifigan_b200 import synth
+import oracle
+
+ALL = ["default_b2_t24", "default_stages_b1_t9", "default_weightnorm_b1_t16",
+       "default_saturated_b1_t16", "default_ragged_b3_t7", "odd_upsample_b1_t20",
+       "small_custom_b3_t33", "default_config1_b1_t256"]
+# the plain-C oracle is slow: keep it to the small cases
+C_CASES = ["default_stages_b1_t9", "default_ragged_b3_t7", "odd_upsample_b1_t20",
+           "small_custom_b3_t33", "default_weightnorm_b1_t16"]
+
+TOL = 2e-6   # fp32 re-association noise between ATen's blocked kernels and a plain sum
+
+
+def _plain(sd):
+    t = {k: torch.from_numpy(v) for k, v in sd.items()}
+    return {k: v.numpy() for k, v in oracle.fold_weight_norm(t).items()}
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_torch_port_matches_reference_golden(manifest, name):
+    cfg, sd, mel = case_inputs(manifest, name)
+    g = load_golden(name)
+    wav = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()},
+                               torch.from_numpy(mel)).numpy()
+    assert wav.shape == g["wav"].shape
+    tol = 2e-5 if "saturated" in name else TOL
+    assert np.abs(wav - g["wav"]).max() <= tol
+
+
+@pytest.mark.parametrize("name", C_CASES)
+def test_c_oracle_matches_reference_golden(manifest, name):
+    cfg, sd, mel = case_inputs(manifest, name)
+    g = load_golden(name)
+    names = [n for n, _ in synth.weight_shapes(cfg)]
+    stages = []
+    wav = oracle.forward_c(cfg, _plain(sd), names, mel, stages=stages)
+    assert wav.shape == g["wav"].shape
+    assert np.abs(wav - g["wav"]).max() <= TOL
+    if "stage0" in g:
+        stride = manifest["stage_stride"]
+        for i, s in enumerate(stages):
+            assert list(s.shape) == list(g[f"stage{i}_shape"])
+            ref = g[f"stage{i}"]
+            err = np.abs(s[:, :, ::stride] - ref).max()
+            assert err <= 1e-5 * max(1.0, np.abs(ref).max()), (i, err)
+
+
+def test_weight_norm_schema_and_fold(manifest):
+    cfg, sd, _ = case_inputs(manifest, "default_weightnorm_b1_t16")
+    g = load_golden("default_weightnorm_b1_t16")
+    assert len(sd) == int(g["n_state_keys"]) == 232
+    assert len(synth.make_weights(cfg, 0)) == 156
+    folded = _plain(sd)
+    assert set(folded) == {n for n, _ in synth.weight_shapes(cfg)}
+    # ConvTranspose1d: dim 0 is C_in
+    assert sd["ups.0.weight_g"].shape == (512, 1, 1)
+
+
+def test_output_length_formula():
+    cfg = synth.DEFAULT_CONFIG
+    for t in (1, 7, 50, 100, 200):
+        assert synth.out_length(cfg, t) == 256 * t          # tests/test_hifigan_generator.py:76-99
+    odd = dict(cfg, upsample_rates=[5, 5, 4, 2], upsample_kernel_sizes=[10, 10, 8, 4])
+    assert synth.out_length(odd, 20) == 4048                 # u*T+1 on the two odd k-u stages
+
+
+def test_flop_model():
+    # 614.105 MFLOP per mel frame for the default config
+    assert abs(synth.flops_per_frame(synth.DEFAULT_CONFIG) / 1e6 - 614.105) < 0.01

@@ -1,0 +1,189 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the
+committed golden vectors of the live reference and against the oracle.
+
+Tolerances (max-abs on the waveform, whose peak is 0.03-0.07 at random init):
+  fp32  2e-5   fp32 FFMA kernels; only summation order differs from ATen
+  tf32  1e-3   north_star's stated bound for the fp32/TF32 mode
+  bf16  5e-3   bf16 operands + bf16 stored activations (log-mel L1 reported by bench)
+"""
+import numpy as np
+import pytest
+import torch
+
+import tts_sambert_hifigan_b200 as pkg
+from tts_sambert_hifigan_b200 import _capi, synth
+
+from conftest import case_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32", "tf32", "bf16"]
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 5e-3}
+CASES = ["default_b2_t24", "default_stages_b1_t9", "default_weightnorm_b1_t16",
+         "default_ragged_b3_t7", "odd_upsample_b1_t20", "small_custom_b3_t33",
+         "default_config1_b1_t256"]
+
+
+def make_gen(cfg, sd, mode):
+    gen = pkg.HiFiGANGenerator(**cfg, mode=mode).to("cuda:0")
+    gen.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return gen
+
+
+def run(gen, mel, stages=None):
+    with torch.no_grad():
+        wav = gen(torch.from_numpy(mel).to("cuda:0"), _stages=stages)
+    torch.cuda.synchronize()
+    return wav.cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", CASES)
+def test_matches_reference_golden(manifest, name, mode):
+    cfg, sd, mel = case_inputs(manifest, name)
+    g = load_golden(name)
+    gen = make_gen(cfg, sd, mode)
+    wav = run(gen, mel)
+    assert wav.shape == g["wav"].shape and wav.dtype == np.float32
+    err = float(np.abs(wav - g["wav"]).max())
+    rel = err / float(np.abs(g["wav"]).max())
+    print(f"{name}[{mode}] max-abs {err:.3e} rel-to-peak {rel:.3e} launches {gen.last_launch_count}")
+    assert err <= TOL[mode]
+    assert gen.last_launch_count > 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_saturated_tanh(manifest, mode):
+    """Weights scaled 2.25x drive a quarter of the samples past |0.9|: the pre-tanh
+    signal is O(1), so operand rounding shows up un-attenuated."""
+    cfg, sd, mel = case_inputs(manifest, "default_saturated_b1_t16")
+    g = load_golden("default_saturated_b1_t16")
+    wav = run(make_gen(cfg, sd, mode), mel)
+    err = float(np.abs(wav - g["wav"]).max())
+    print(f"saturated[{mode}] max-abs {err:.3e}")
+    assert np.abs(wav).max() <= 1.0
+    assert err <= {"fp32": 2e-4, "tf32": 2e-2, "bf16": 1.5e-1}[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_stage_boundaries(manifest, mode):
+    """Stage-boundary activations (what forward hooks on conv_pre / ups[i] / mrfs[i]
+    see in the reference), time-subsampled in the golden file."""
+    name = "default_stages_b1_t9"
+    cfg, sd, mel = case_inputs(manifest, name)
+    g = load_golden(name)
+    stages = []
+    run(make_gen(cfg, sd, mode), mel, stages=stages)
+    stride = manifest["stage_stride"]
+    assert len(stages) == 2 * len(cfg["upsample_rates"]) + 1
+    rtol = {"fp32": 1e-5, "tf32": 4e-3, "bf16": 3e-2}[mode]
+    for i, s in enumerate(stages):
+        s = s.cpu().numpy()
+        ref = g[f"stage{i}"]
+        assert list(s.shape) == list(g[f"stage{i}_shape"])
+        err = float(np.abs(s[:, :, ::stride] - ref).max())
+        peak = float(np.abs(ref).max())
+        print(f"stage{i}[{mode}] max-abs {err:.3e} peak {peak:.3e}")
+        assert err <= rtol * peak, (i, err, peak)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_config2_against_oracle(mode):
+    """BASELINE.json configs[1]: batch 16 x 172 frames, fp32/TF32, <= 1e-3."""
+    import oracle
+    cfg = synth.DEFAULT_CONFIG
+    sd = synth.make_weights(cfg, 0)
+    mel = synth.make_mel(1, 16, 80, 172)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()},
+                               torch.from_numpy(mel)).numpy()
+    wav = run(make_gen(cfg, sd, mode), mel)
+    err = float(np.abs(wav - ref).max())
+    print(f"config2[{mode}] max-abs {err:.3e} rel-to-peak {err / np.abs(ref).max():.3e}")
+    assert wav.shape == (16, 1, 172 * 256)
+    assert err <= min(1e-3, TOL[mode] * 5)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_reference_shape_and_range_tests(mode):
+    """reference tests/test_hifigan_generator.py:40-126 and
+    tests/test_hifigan_integration.py:26-54, on the CUDA path."""
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 9), mode)
+    for B, T in [(2, 100), (1, 50), (1, 200), (4, 100), (8, 100), (1, 10), (1, 1)]:
+        wav = run(gen, synth.make_mel(B * 1000 + T, B, 80, T))
+        assert wav.shape == (B, 1, T * 256)
+        assert wav.dtype == np.float32
+        assert wav.min() >= -1.0 and wav.max() <= 1.0
+        assert np.isfinite(wav).all() and np.abs(wav).max() > 0
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_batch_independence_and_determinism(mode):
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 2), mode)
+    mel = synth.make_mel(4, 3, 80, 37)
+    a = run(gen, mel)
+    b = run(gen, mel)
+    assert np.array_equal(a, b)                       # bit-deterministic
+    for i in range(3):
+        one = run(gen, mel[i:i + 1])
+        assert np.array_equal(one[0], a[i])           # no cross-utterance state
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_host_buffer_path_equals_device_path(mode):
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 2), mode)
+    mel = synth.make_mel(8, 2, 80, 33)
+    dev = run(gen, mel)
+    with torch.no_grad():
+        host = gen(torch.from_numpy(mel))             # CPU tensor in -> CPU tensor out
+    assert not host.is_cuda
+    assert np.array_equal(host.numpy(), dev)
+
+
+def test_debug_prints_match_reference(manifest, capsys):
+    gen = pkg.HiFiGANGenerator(debug_shapes=True, mode="fp32").to("cuda:0")
+    with torch.no_grad():
+        gen(torch.zeros(1, 80, 10, device="cuda:0"))
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("[HiFiGANGenerator]")]
+    want = [l for l in manifest["debug_print_lines"] if l.startswith("[HiFiGANGenerator]")]
+    assert out == want
+
+
+def test_c_abi_error_codes():
+    cfg = _capi.make_config(**synth.DEFAULT_CONFIG)
+    h = _capi.Handle(cfg)
+    with pytest.raises(_capi.HfgError) as e:           # nothing loaded yet
+        h.commit()
+    assert e.value.code == _capi.ERR_STATE and "conv_pre.weight" in str(e.value)
+    sd = synth.make_weights(synth.DEFAULT_CONFIG, 1)
+    bad = np.zeros((3, 3, 3), np.float32)
+    h.set_weight("conv_pre.weight", bad.ctypes.data, bad.shape)
+    for k, v in sd.items():
+        if k != "conv_pre.weight":
+            h.set_weight(k, v.ctypes.data, v.shape)
+    with pytest.raises(_capi.HfgError) as e:           # wrong shape is named
+        h.commit()
+    assert e.value.code == _capi.ERR_INVALID
+    with pytest.raises(_capi.HfgError) as e:
+        h.set_weight("conv_pre.gamma", bad.ctypes.data, bad.shape)
+    assert e.value.code == _capi.ERR_INVALID
+    w = sd["conv_pre.weight"]
+    h.set_weight("conv_pre.weight", w.ctypes.data, w.shape)
+    h.commit()
+    assert h.out_len(100) == 25600
+    need = h.workspace_bytes(1, 8, _capi.MODE_FP32)
+    mel = torch.zeros(1, 80, 8, device="cuda:0")
+    wav = torch.empty(1, 1, 2048, device="cuda:0")
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda:0")
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward(mel.data_ptr(), 1, 8, wav.data_ptr(), ws.data_ptr(), need - 1, _capi.MODE_FP32, 0)
+    assert e.value.code == _capi.ERR_WORKSPACE
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward(mel.data_ptr(), 1, 8, wav.data_ptr(), ws.data_ptr(), need, 7, 0)
+    assert e.value.code == _capi.ERR_INVALID
+    h.forward(mel.data_ptr(), 1, 8, wav.data_ptr(), ws.data_ptr(), need, _capi.MODE_FP32, 0)
+    torch.cuda.synchronize()
+    assert h.last_launch_count() > 0
+    h.close()

@@ -1,0 +1,515 @@
+// C-ABI implementation (include/hfg.h): handle, state_dict ingestion, weight-norm
+// folding, weight repacking, workspace planning and the per-mode launch plans.
+#include "../../include/hfg.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fp32_kernels.cuh"
+#include "model.h"
+#include "tc_path.cuh"
+
+namespace hfg {
+
+// ---------------------------------------------------------------------------
+// state_dict ingestion
+// ---------------------------------------------------------------------------
+
+static const HostTensor& need(const hfg_handle* h, const std::string& key) {
+    auto it = h->sd.find(key);
+    if (it == h->sd.end()) throw StatusError(HFG_ERR_STATE, "missing state_dict key: " + key);
+    return it->second;
+}
+
+// Plain weight of layer `prefix` ("ups.0", "mrfs.0.resblocks.1.convs1.2", ...):
+// either `.weight`, or g*v/||v|| folded from `.weight_g`/`.weight_v`
+// (nn.utils.weight_norm, dim=0; reference models/hifigan.py:274-283).
+static HostTensor plain_weight(const hfg_handle* h, const std::string& prefix,
+                               const std::vector<int64_t>& want) {
+    HostTensor w;
+    auto it = h->sd.find(prefix + ".weight");
+    if (it != h->sd.end()) {
+        w = it->second;
+    } else {
+        const HostTensor& g = need(h, prefix + ".weight_g");
+        const HostTensor& v = need(h, prefix + ".weight_v");
+        if (v.shape.size() != 3 || g.numel() != v.shape[0])
+            throw StatusError(HFG_ERR_INVALID, "weight_g/weight_v shape mismatch at " + prefix);
+        w = v;
+        const size_t inner = (size_t)(v.shape[1] * v.shape[2]);
+        for (int64_t i = 0; i < v.shape[0]; ++i) {
+            double ss = 0.0;
+            for (size_t e = 0; e < inner; ++e) {
+                const double x = v.data[i * inner + e];
+                ss += x * x;
+            }
+            const double s = (double)g.data[i] / std::sqrt(ss);
+            for (size_t e = 0; e < inner; ++e)
+                w.data[i * inner + e] = (float)(s * (double)v.data[i * inner + e]);
+        }
+    }
+    if (w.shape != want) {
+        std::string msg = "shape mismatch for " + prefix + ".weight: got [";
+        for (auto d : w.shape) msg += std::to_string(d) + ",";
+        msg += "] want [";
+        for (auto d : want) msg += std::to_string(d) + ",";
+        throw StatusError(HFG_ERR_INVALID, msg + "]");
+    }
+    return w;
+}
+
+static HostTensor plain_bias(const hfg_handle* h, const std::string& prefix, int64_t n) {
+    const HostTensor& b = need(h, prefix + ".bias");
+    if (b.numel() != n) throw StatusError(HFG_ERR_INVALID, "shape mismatch for " + prefix + ".bias");
+    return b;
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static int pick_rco(int cout) { return cout >= 128 ? 8 : (cout >= 64 ? 4 : 2); }
+
+// Conv1d weight [Cout, Cin, k] -> fp32 tile layout [k][CinPad][CoutPad]
+static void pack_conv_fp32(hfg_handle* h, ConvLayer& L, const HostTensor& w, const HostTensor& b) {
+    L.rco = pick_rco(L.cout);
+    L.cin_pad = round_up(L.cin, kTileCi);
+    L.cout_pad = round_up(L.cout, L.rco * 16);
+    std::vector<float> p((size_t)L.k * L.cin_pad * L.cout_pad, 0.f);
+    for (int co = 0; co < L.cout; ++co)
+        for (int ci = 0; ci < L.cin; ++ci)
+            for (int j = 0; j < L.k; ++j)
+                p[((size_t)j * L.cin_pad + ci) * L.cout_pad + co] =
+                    w.data[((size_t)co * L.cin + ci) * L.k + j];
+    L.w_fp32 = h->upload(p);
+    L.bias = h->upload(b.data);
+}
+
+// ConvTranspose1d weight [Cin, Cout, k] -> polyphase [u][ceil(k/u)][CinPad][CoutPad]
+static void pack_up_fp32(hfg_handle* h, UpLayer& L, const HostTensor& w, const HostTensor& b) {
+    L.rco = pick_rco(L.cout);
+    L.cin_pad = round_up(L.cin, kTileCi);
+    L.cout_pad = round_up(L.cout, L.rco * 16);
+    L.taps_max = (L.k + L.u - 1) / L.u;
+    std::vector<float> p((size_t)L.u * L.taps_max * L.cin_pad * L.cout_pad, 0.f);
+    for (int r = 0; r < L.u; ++r)
+        for (int m = 0; r + m * L.u < L.k; ++m)
+            for (int ci = 0; ci < L.cin; ++ci)
+                for (int co = 0; co < L.cout; ++co)
+                    p[(((size_t)r * L.taps_max + m) * L.cin_pad + ci) * L.cout_pad + co] =
+                        w.data[((size_t)ci * L.cout + co) * L.k + r + m * L.u];
+    L.w_fp32 = h->upload(p);
+    L.bias = h->upload(b.data);
+}
+
+static void commit(hfg_handle* h) {
+    const hfg_config& c = h->cfg;
+    h->free_device_weights();
+    h->ups.clear();
+    h->mrfs.clear();
+
+    // conv_pre: Conv1d(n_mels, c0, 7, padding=3)   (reference models/hifigan.py:177-183)
+    h->pre = ConvLayer{};
+    h->pre.cin = c.n_mels; h->pre.cout = c.upsample_initial_channel;
+    h->pre.k = 7; h->pre.dil = 1; h->pre.pad = 3;
+    {
+        HostTensor w = plain_weight(h, "conv_pre", {h->pre.cout, h->pre.cin, 7});
+        HostTensor b = plain_bias(h, "conv_pre", h->pre.cout);
+        pack_conv_fp32(h, h->pre, w, b);
+        tc_pack_conv(h, h->pre, w, b);
+    }
+    int C = c.upsample_initial_channel;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        UpLayer U{};
+        U.cin = C; U.cout = C / 2;
+        U.k = c.upsample_kernel_sizes[i]; U.u = c.upsample_rates[i];
+        U.p = (U.k - U.u) / 2;                       // reference :201
+        const std::string up = "ups." + std::to_string(i);
+        HostTensor w = plain_weight(h, up, {U.cin, U.cout, U.k});
+        HostTensor b = plain_bias(h, up, U.cout);
+        pack_up_fp32(h, U, w, b);
+        tc_pack_up(h, U, w, b);
+        h->ups.push_back(U);
+        C = U.cout;
+        std::vector<std::vector<PairLayers>> mrf;
+        for (int j = 0; j < c.num_resblocks; ++j) {
+            std::vector<PairLayers> rb;
+            const int k = c.resblock_kernel_sizes[j];
+            for (int l = 0; l < c.num_dilations[j]; ++l) {
+                const int d = c.resblock_dilations[j][l];
+                PairLayers P{};
+                const std::string base =
+                    "mrfs." + std::to_string(i) + ".resblocks." + std::to_string(j) + ".";
+                // convs1[l]: dilation d, padding (k*d-d)/2   (reference :52-59, 21-23)
+                P.c1.cin = P.c1.cout = C; P.c1.k = k; P.c1.dil = d; P.c1.pad = (k * d - d) / 2;
+                // convs2[l]: dilation 1, padding (k-1)/2     (reference :61-69)
+                P.c2.cin = P.c2.cout = C; P.c2.k = k; P.c2.dil = 1; P.c2.pad = (k - 1) / 2;
+                const std::string n1 = base + "convs1." + std::to_string(l);
+                const std::string n2 = base + "convs2." + std::to_string(l);
+                HostTensor w1 = plain_weight(h, n1, {C, C, k}), b1 = plain_bias(h, n1, C);
+                HostTensor w2 = plain_weight(h, n2, {C, C, k}), b2 = plain_bias(h, n2, C);
+                pack_conv_fp32(h, P.c1, w1, b1);
+                pack_conv_fp32(h, P.c2, w2, b2);
+                tc_pack_conv(h, P.c1, w1, b1);
+                tc_pack_conv(h, P.c2, w2, b2);
+                rb.push_back(P);
+            }
+            mrf.push_back(rb);
+        }
+        h->mrfs.push_back(mrf);
+    }
+    // conv_post: Conv1d(C_last, 1, 7, padding=3)   (reference :215-222)
+    {
+        HostTensor w = plain_weight(h, "conv_post", {1, C, 7});
+        HostTensor b = plain_bias(h, "conv_post", 1);
+        h->post_cin = C;
+        h->post_w = h->upload(w.data);     // [1][Cin][7] == [Cin][7]
+        h->post_b = h->upload(b.data);
+        tc_pack_post(h, w, b);
+    }
+    h->committed = true;
+}
+
+// ---------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------
+
+static int64_t up_len(const UpLayer& U, int64_t t) { return (t - 1) * U.u - 2 * U.p + U.k; }
+
+static void stage_geometry(const hfg_handle* h, int T, std::vector<int>& C, std::vector<int64_t>& L) {
+    C.assign(1, h->cfg.upsample_initial_channel);
+    L.assign(1, T);
+    for (auto& U : h->ups) {
+        C.push_back(U.cout);
+        L.push_back(up_len(U, L.back()));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// fp32 launch plan
+// ---------------------------------------------------------------------------
+
+static void launch_conv_fp32(hfg_handle* h, cudaStream_t st, const ConvArgs& a, int rco, int nq, int B) {
+    const int tco = rco * 16;
+    const int span = (a.taps_max - 1) * (a.dil < 0 ? -a.dil : a.dil);
+    const size_t smem = sizeof(float) * ((size_t)kTileCi * (kTileT + span) + (size_t)a.taps_max * kTileCi * tco);
+    dim3 grid((nq + kTileT - 1) / kTileT, a.phases * a.co_tiles, B);
+    switch (rco) {
+        case 8: conv_tile_fp32<8><<<grid, kThreads, smem, st>>>(a); break;
+        case 4: conv_tile_fp32<4><<<grid, kThreads, smem, st>>>(a); break;
+        default: conv_tile_fp32<2><<<grid, kThreads, smem, st>>>(a); break;
+    }
+    h->launches++;
+    check_cuda(cudaGetLastError(), "conv_tile_fp32 launch");
+}
+
+static ConvArgs conv_args(const ConvLayer& L, const float* x, float* y, int T, float slope) {
+    ConvArgs a{};
+    a.x = x; a.w = L.w_fp32; a.bias = L.bias; a.res = nullptr; a.y = y;
+    a.Cin = L.cin; a.CinPad = L.cin_pad; a.Tin = T;
+    a.Cout = L.cout; a.CoutPad = L.cout_pad; a.Tout = T;
+    a.taps_max = L.k; a.k = L.k; a.u = 1; a.dil = L.dil; a.pad = L.pad;
+    a.out_stride = 1; a.out_off = 0; a.phases = 1;
+    a.co_tiles = L.cout_pad / (L.rco * 16);
+    a.slope = slope; a.epi_flags = 0; a.div = 1.f;
+    return a;
+}
+
+static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws,
+                         cudaStream_t st, float* const* stage_out) {
+    std::vector<int> C;
+    std::vector<int64_t> L;
+    stage_geometry(h, T, C, L);
+    size_t emax = 0;
+    for (size_t i = 0; i < C.size(); ++i) emax = std::max(emax, (size_t)B * C[i] * L[i]);
+    const size_t stride = (emax * sizeof(float) + 255) / 256 * 256;
+    float* bufX = (float*)(ws);
+    float* bufR = (float*)(ws + stride);
+    float* bufH = (float*)(ws + 2 * stride);
+    float* bufA = (float*)(ws + 3 * stride);
+    float* bufB = (float*)(ws + 4 * stride);
+    const float slope = 0.1f;
+    const int n_rb = h->cfg.num_resblocks;
+    auto dump = [&](int idx, const float* src, size_t n) {
+        if (stage_out && stage_out[idx])
+            check_cuda(cudaMemcpyAsync(stage_out[idx], src, n * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st), "stage dump");
+    };
+
+    // conv_pre (reference :238), no activation on the mel
+    float* cur = bufA;
+    launch_conv_fp32(h, st, conv_args(h->pre, mel, cur, T, 1.0f), h->pre.rco, T, B);
+    dump(0, cur, (size_t)B * C[0] * L[0]);
+
+    for (size_t i = 0; i < h->ups.size(); ++i) {
+        const UpLayer& U = h->ups[i];
+        const int Tin = (int)L[i], Tout = (int)L[i + 1];
+        // x = ups[i](leaky_relu(x))  (reference :244-245)
+        ConvArgs a{};
+        a.x = cur; a.w = U.w_fp32; a.bias = U.bias; a.res = nullptr; a.y = bufX;
+        a.Cin = U.cin; a.CinPad = U.cin_pad; a.Tin = Tin;
+        a.Cout = U.cout; a.CoutPad = U.cout_pad; a.Tout = Tout;
+        a.taps_max = U.taps_max; a.k = U.k; a.u = U.u; a.dil = -1; a.pad = 0;
+        a.out_stride = U.u; a.out_off = -U.p; a.phases = U.u;
+        a.co_tiles = U.cout_pad / (U.rco * 16);
+        a.slope = slope; a.epi_flags = 0; a.div = 1.f;
+        const int nq = (Tout - 1 + U.p) / U.u + 1;
+        launch_conv_fp32(h, st, a, U.rco, nq, B);
+        const size_t n = (size_t)B * U.cout * Tout;
+        dump(1 + 2 * (int)i, bufX, n);
+
+        // MRF (reference :116-131)
+        float* acc = (cur == bufA) ? bufB : bufA;
+        for (int j = 0; j < n_rb; ++j) {
+            const auto& rb = h->mrfs[i][j];
+            const float* r = bufX;
+            for (size_t l = 0; l < rb.size(); ++l) {
+                const bool last = (l + 1 == rb.size());
+                launch_conv_fp32(h, st, conv_args(rb[l].c1, r, bufH, Tout, slope), rb[l].c1.rco, Tout, B);
+                ConvArgs a2 = conv_args(rb[l].c2, bufH, last ? acc : bufR, Tout, slope);
+                a2.res = r;
+                if (last) {
+                    if (j > 0) a2.epi_flags |= EPI_ACC_READ;
+                    if (j == n_rb - 1) { a2.epi_flags |= EPI_ACC_DIV; a2.div = (float)n_rb; }
+                }
+                launch_conv_fp32(h, st, a2, rb[l].c2.rco, Tout, B);
+                r = bufR;
+            }
+        }
+        cur = acc;
+        dump(2 + 2 * (int)i, cur, n);
+    }
+    // wav = tanh(conv_post(leaky_relu(x)))  (reference :254-256)
+    PostArgs p{};
+    p.x = cur; p.w = h->post_w; p.bias = h->post_b; p.y = wav;
+    p.Cin = h->post_cin; p.T = (int)L.back(); p.k = 7; p.pad = 3; p.slope = slope;
+    dim3 grid((p.T + 255) / 256, B);
+    conv_post_tanh_fp32<<<grid, 256, sizeof(float) * p.Cin * p.k, st>>>(p);
+    h->launches++;
+    check_cuda(cudaGetLastError(), "conv_post launch");
+}
+
+static size_t workspace_fp32(const hfg_handle* h, int B, int T) {
+    std::vector<int> C;
+    std::vector<int64_t> L;
+    stage_geometry(h, T, C, L);
+    size_t emax = 0;
+    for (size_t i = 0; i < C.size(); ++i) emax = std::max(emax, (size_t)B * C[i] * L[i]);
+    const size_t stride = (emax * sizeof(float) + 255) / 256 * 256;
+    return 5 * stride;
+}
+
+static void validate_config(const hfg_config& c) {
+    auto bad = [](const std::string& m) { throw StatusError(HFG_ERR_INVALID, m); };
+    if (c.n_mels <= 0) bad("n_mels must be positive");
+    if (c.num_upsamples <= 0 || c.num_upsamples > HFG_MAX_STAGES) bad("num_upsamples out of range");
+    if (c.num_resblocks <= 0 || c.num_resblocks > HFG_MAX_STAGES) bad("num_resblocks out of range");
+    if (c.upsample_initial_channel <= 0 ||
+        (c.upsample_initial_channel >> c.num_upsamples) <= 0 ||
+        ((c.upsample_initial_channel >> c.num_upsamples) << c.num_upsamples) != c.upsample_initial_channel)
+        bad("upsample_initial_channel must be divisible by 2^num_upsamples");
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        if (c.upsample_rates[i] <= 0 || c.upsample_kernel_sizes[i] < c.upsample_rates[i])
+            bad("upsample kernel size must be >= rate > 0");
+    }
+    for (int j = 0; j < c.num_resblocks; ++j) {
+        if (c.resblock_kernel_sizes[j] <= 0 || c.resblock_kernel_sizes[j] % 2 == 0)
+            bad("resblock kernel sizes must be odd (reference 'same' padding, models/hifigan.py:21-23)");
+        if (c.num_dilations[j] <= 0 || c.num_dilations[j] > HFG_MAX_STAGES) bad("num_dilations out of range");
+        for (int l = 0; l < c.num_dilations[j]; ++l)
+            if (c.resblock_dilations[j][l] <= 0) bad("dilations must be positive");
+    }
+}
+
+static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav, void* ws,
+                       size_t ws_bytes, int mode, cudaStream_t st, float* const* stage_out) {
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed (call hfg_commit_weights)");
+    if (!mel || !wav) throw StatusError(HFG_ERR_INVALID, "null mel/wav pointer");
+    if (B <= 0 || T <= 0) throw StatusError(HFG_ERR_INVALID, "batch and frames must be positive");
+    if (B > 65535) throw StatusError(HFG_ERR_INVALID, "batch > 65535: split the call");
+    size_t need_bytes = 0;
+    if (mode == HFG_MODE_FP32) need_bytes = workspace_fp32(h, B, T);
+    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) need_bytes = tc_workspace_bytes(h, B, T, mode);
+    else throw StatusError(HFG_ERR_INVALID, "unknown mode");
+    if (!ws || ws_bytes < need_bytes) throw StatusError(HFG_ERR_WORKSPACE, "workspace too small");
+    if (((uintptr_t)ws & 255) != 0) throw StatusError(HFG_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+    h->launches = 0;
+    if (mode == HFG_MODE_FP32) forward_fp32(h, mel, B, T, wav, (char*)ws, st, stage_out);
+    else tc_forward(h, mel, B, T, wav, (char*)ws, mode, st, stage_out);
+}
+
+}  // namespace hfg
+
+using namespace hfg;
+
+#define HFG_TRY(h)  try {
+#define HFG_CATCH(h)                                                         \
+    } catch (const StatusError& e) {                                         \
+        if (h) (h)->last_error = e.what();                                   \
+        return e.code;                                                       \
+    } catch (const std::exception& e) {                                      \
+        if (h) (h)->last_error = e.what();                                   \
+        return HFG_ERR_INVALID;                                              \
+    }                                                                        \
+    return HFG_OK;
+
+extern "C" {
+
+int hfg_abi_version(void) { return HFG_ABI_VERSION; }
+
+int hfg_create(const hfg_config* cfg, hfg_handle** out) {
+    if (!cfg || !out) return HFG_ERR_INVALID;
+    *out = nullptr;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return HFG_ERR_CUDA; }
+    hfg_handle* h = nullptr;
+    try {
+        validate_config(*cfg);
+        h = new hfg_handle();
+        h->cfg = *cfg;
+        h->device = dev;
+        cudaDeviceProp prop{};
+        check_cuda(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+        h->sm_count = prop.multiProcessorCount;
+        h->cc_major = prop.major;
+        configure_kernels(h);
+    } catch (const StatusError& e) {
+        delete h;
+        return e.code;
+    } catch (...) {
+        delete h;
+        return HFG_ERR_INVALID;
+    }
+    *out = h;
+    return HFG_OK;
+}
+
+void hfg_destroy(hfg_handle* h) {
+    if (!h) return;
+    h->free_device_weights();
+    h->free_host_path();
+    delete h;
+}
+
+const char* hfg_last_error(const hfg_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int hfg_set_weight(hfg_handle* h, const char* name, const float* data, const int64_t* shape,
+                   int32_t ndim) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!name || !data || !shape || ndim < 1 || ndim > 3)
+        throw StatusError(HFG_ERR_INVALID, "hfg_set_weight: bad argument");
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] <= 0) throw StatusError(HFG_ERR_INVALID, "hfg_set_weight: non-positive dim");
+        t.shape.push_back(shape[i]);
+        n *= shape[i];
+    }
+    t.data.assign(data, data + n);
+    const std::string key(name);
+    // plain and weight-normed forms of the same layer are mutually exclusive
+    auto ends = [&](const char* s) {
+        const size_t l = strlen(s);
+        return key.size() >= l && key.compare(key.size() - l, l, s) == 0;
+    };
+    if (ends(".weight")) {
+        h->sd.erase(key + "_g");
+        h->sd.erase(key + "_v");
+    } else if (ends(".weight_g") || ends(".weight_v")) {
+        h->sd.erase(key.substr(0, key.size() - 2));
+    } else if (!ends(".bias")) {
+        throw StatusError(HFG_ERR_INVALID, "unexpected state_dict key: " + key);
+    }
+    h->sd[key] = std::move(t);
+    h->committed = false;
+    HFG_CATCH(h)
+}
+
+int hfg_commit_weights(hfg_handle* h) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    check_cuda(cudaSetDevice(h->device), "cudaSetDevice");
+    commit(h);
+    HFG_CATCH(h)
+}
+
+int hfg_out_len(const hfg_handle* h, int32_t frames, int64_t* out_len) {
+    if (!h || !out_len || frames <= 0) return HFG_ERR_INVALID;
+    int64_t t = frames;
+    const hfg_config& c = h->cfg;
+    for (int i = 0; i < c.num_upsamples; ++i) {
+        const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+        t = (t - 1) * u - 2 * ((k - u) / 2) + k;
+    }
+    *out_len = t;
+    return HFG_OK;
+}
+
+int hfg_workspace_bytes(const hfg_handle* hc, int32_t batch, int32_t frames, int32_t mode,
+                        size_t* bytes) {
+    hfg_handle* h = const_cast<hfg_handle*>(hc);
+    if (!h || !bytes) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
+    if (batch <= 0 || frames <= 0) throw StatusError(HFG_ERR_INVALID, "batch and frames must be positive");
+    if (mode == HFG_MODE_FP32) *bytes = workspace_fp32(h, batch, frames);
+    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) *bytes = tc_workspace_bytes(h, batch, frames, mode);
+    else throw StatusError(HFG_ERR_INVALID, "unknown mode");
+    HFG_CATCH(h)
+}
+
+int hfg_forward(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames, float* wav_dev,
+                void* workspace_dev, size_t workspace_bytes, int32_t mode, void* stream) {
+    return hfg_forward_stages(h, mel_dev, batch, frames, wav_dev, workspace_dev, workspace_bytes,
+                              mode, stream, nullptr);
+}
+
+int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames,
+                       float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
+                       void* stream, float* const* stage_out_dev) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    do_forward(h, mel_dev, batch, frames, wav_dev, workspace_dev, workspace_bytes, mode,
+               (cudaStream_t)stream, stage_out_dev);
+    HFG_CATCH(h)
+}
+
+int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
+                     float* wav_host, int32_t mode) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
+    if (!mel_host || !wav_host || batch <= 0 || frames <= 0)
+        throw StatusError(HFG_ERR_INVALID, "hfg_forward_host: bad argument");
+    check_cuda(cudaSetDevice(h->device), "cudaSetDevice");
+    int64_t tout = 0;
+    hfg_out_len(h, frames, &tout);
+    const size_t mel_bytes = sizeof(float) * (size_t)batch * h->cfg.n_mels * frames;
+    const size_t wav_bytes = sizeof(float) * (size_t)batch * tout;
+    size_t ws_bytes = 0;
+    if (mode == HFG_MODE_FP32) ws_bytes = workspace_fp32(h, batch, frames);
+    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) ws_bytes = tc_workspace_bytes(h, batch, frames, mode);
+    else throw StatusError(HFG_ERR_INVALID, "unknown mode");
+    h->ensure_host_path(mel_bytes, wav_bytes, ws_bytes);
+    memcpy(h->pin_mel, mel_host, mel_bytes);
+    check_cuda(cudaMemcpyAsync(h->dev_mel, h->pin_mel, mel_bytes, cudaMemcpyHostToDevice, h->stream), "H2D mel");
+    do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+    check_cuda(cudaMemcpyAsync(h->pin_wav, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
+    check_cuda(cudaStreamSynchronize(h->stream), "stream sync");
+    memcpy(wav_host, h->pin_wav, wav_bytes);
+    HFG_CATCH(h)
+}
+
+int hfg_last_launch_count(const hfg_handle* h, int64_t* launches) {
+    if (!h || !launches) return HFG_ERR_INVALID;
+    *launches = h->launches;
+    return HFG_OK;
+}
+
+}  // extern "C"

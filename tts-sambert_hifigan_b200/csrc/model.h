@@ -1,0 +1,145 @@
+// Host-side model state behind an hfg_handle.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hfg.h"
+
+namespace hfg {
+
+struct StatusError : std::runtime_error {
+    int code;
+    StatusError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+inline void check_cuda(cudaError_t e, const char* what) {
+    if (e != cudaSuccess)
+        throw StatusError(HFG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (auto d : shape) n *= d;
+        return n;
+    }
+};
+
+// Tensor-core operand pack of one conv (tc_path.cuh): per tap, an [N=Cout][K=Cin]
+// K-major matrix in the UMMA no-swizzle "interleaved" canonical layout.
+struct TcPack {
+    void* w_bf16 = nullptr;   // bf16 operand tiles
+    void* w_tf32 = nullptr;   // fp32 (consumed as tf32) operand tiles
+    bool ok = false;          // layer shape is covered by the tensor-core path
+};
+
+struct ConvLayer {
+    int cin = 0, cout = 0, k = 0, dil = 1, pad = 0;
+    int cin_pad = 0, cout_pad = 0, rco = 2;
+    float* w_fp32 = nullptr;  // [k][cin_pad][cout_pad]
+    float* bias = nullptr;    // [cout]
+    TcPack tc;
+};
+
+struct UpLayer {
+    int cin = 0, cout = 0, k = 0, u = 1, p = 0, taps_max = 0;
+    int cin_pad = 0, cout_pad = 0, rco = 2;
+    float* w_fp32 = nullptr;  // [u][taps_max][cin_pad][cout_pad]
+    float* bias = nullptr;
+    TcPack tc;
+};
+
+struct PairLayers {
+    ConvLayer c1, c2;
+};
+
+}  // namespace hfg
+
+struct hfg_handle {
+    hfg_config cfg{};
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0;
+    bool committed = false;
+    std::string last_error;
+    int64_t launches = 0;
+
+    std::map<std::string, hfg::HostTensor> sd;   // raw state_dict as set by the caller
+
+    hfg::ConvLayer pre;
+    std::vector<hfg::UpLayer> ups;
+    std::vector<std::vector<std::vector<hfg::PairLayers>>> mrfs;   // [stage][resblock][pair]
+    int post_cin = 0;
+    float* post_w = nullptr;
+    float* post_b = nullptr;
+    hfg::TcPack post_tc;
+
+    std::vector<void*> device_allocs;
+
+    // hfg_forward_host resources
+    cudaStream_t stream = nullptr;
+    float* pin_mel = nullptr; size_t pin_mel_bytes = 0;
+    float* pin_wav = nullptr; size_t pin_wav_bytes = 0;
+    float* dev_mel = nullptr; size_t dev_mel_bytes = 0;
+    float* dev_wav = nullptr; size_t dev_wav_bytes = 0;
+    void* dev_ws = nullptr;   size_t dev_ws_bytes = 0;
+
+    void* alloc_device(size_t bytes) {
+        void* p = nullptr;
+        hfg::check_cuda(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc(weights)");
+        device_allocs.push_back(p);
+        return p;
+    }
+    template <typename T>
+    T* upload(const std::vector<T>& v) {
+        T* p = (T*)alloc_device(v.size() * sizeof(T));
+        hfg::check_cuda(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice),
+                        "cudaMemcpy(weights)");
+        return p;
+    }
+    void free_device_weights() {
+        for (void* p : device_allocs) cudaFree(p);
+        device_allocs.clear();
+        committed = false;
+    }
+    void ensure_host_path(size_t mel_bytes, size_t wav_bytes, size_t ws_bytes) {
+        using hfg::check_cuda;
+        if (!stream) check_cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        auto grow_pin = [](float*& p, size_t& have, size_t want) {
+            if (have >= want) return;
+            if (p) cudaFreeHost(p);
+            p = nullptr; have = 0;
+            check_cuda(cudaMallocHost((void**)&p, want), "cudaMallocHost");
+            have = want;
+        };
+        auto grow_dev = [](void** p, size_t& have, size_t want) {
+            if (have >= want) return;
+            if (*p) cudaFree(*p);
+            *p = nullptr; have = 0;
+            check_cuda(cudaMalloc(p, want), "cudaMalloc");
+            have = want;
+        };
+        grow_pin(pin_mel, pin_mel_bytes, mel_bytes);
+        grow_pin(pin_wav, pin_wav_bytes, wav_bytes);
+        grow_dev((void**)&dev_mel, dev_mel_bytes, mel_bytes);
+        grow_dev((void**)&dev_wav, dev_wav_bytes, wav_bytes);
+        grow_dev(&dev_ws, dev_ws_bytes, ws_bytes);
+    }
+    void free_host_path() {
+        if (pin_mel) cudaFreeHost(pin_mel);
+        if (pin_wav) cudaFreeHost(pin_wav);
+        if (dev_mel) cudaFree(dev_mel);
+        if (dev_wav) cudaFree(dev_wav);
+        if (dev_ws) cudaFree(dev_ws);
+        if (stream) cudaStreamDestroy(stream);
+        pin_mel = pin_wav = dev_mel = dev_wav = nullptr;
+        dev_ws = nullptr; stream = nullptr;
+        pin_mel_bytes = pin_wav_bytes = dev_mel_bytes = dev_wav_bytes = dev_ws_bytes = 0;
+    }
+};

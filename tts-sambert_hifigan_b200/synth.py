@@ -148,3 +148,26 @@ def flops_per_frame(cfg: dict) -> float:
     cl = c0 // (2 ** len(cfg["upsample_rates"]))
     mac += scale * cl * 7
     return 2.0 * mac
+
+
+def make_weightnorm_weights(cfg: dict, seed: int) -> Dict[str, np.ndarray]:
+    """The 232-key weight-normed schema (reference models/hifigan.py:274-283:
+    `weight` -> `weight_g` [C0,1,1] + `weight_v` on ups / convs1 / convs2 only),
+    with g perturbed by a seeded factor in [0.75, 1.25] so that folding
+    g * v / ||v|| is not the identity.  Mirrors tests/golden/make_golden.py."""
+    plain = make_weights(cfg, seed)
+    out: Dict[str, np.ndarray] = {}
+    g_keys = []
+    for name, w in plain.items():
+        if name.endswith(".weight") and not name.startswith(("conv_pre", "conv_post")):
+            base = name[: -len("weight")]
+            norm = np.sqrt((w.astype(np.float64) ** 2).sum(axis=(1, 2), keepdims=True))
+            out[base + "weight_g"] = norm.astype(np.float32)
+            out[base + "weight_v"] = w
+            g_keys.append(base + "weight_g")
+        else:
+            out[name] = w
+    for i, k in enumerate(sorted(g_keys)):
+        scale = uniform(seed, out[k].shape, 0.25, stream=1000 + i) + np.float32(1.0)
+        out[k] = (out[k] * scale).astype(np.float32)
+    return out
