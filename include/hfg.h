@@ -119,6 +119,15 @@ int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32
 int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
                      float* wav_host, int32_t mode);
 
+/* Per-launch device timing.  When enabled, every kernel launch of hfg_forward*
+ * is bracketed by a CUDA event pair on the launching stream; hfg_get_profile
+ * synchronises and returns a JSON array, one entry per kernel label:
+ *   [{"kernel":"mrf0","launches":18,"ms":..,"flops":..,"bytes":..}, ...]
+ * (flops / bytes are the ALGORITHMIC work of those launches).  Call with
+ * buf == NULL to query the size.  Used by bench.py for the roofline figures. */
+int hfg_set_profiling(hfg_handle* h, int32_t enable);
+int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed);
+
 /* Number of kernels the last hfg_forward* call on this handle launched. */
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches);
 

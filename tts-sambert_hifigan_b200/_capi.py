@@ -16,6 +16,7 @@ SYMBOLS = [
     "hfg_abi_version", "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_weight",
     "hfg_commit_weights", "hfg_out_len", "hfg_workspace_bytes", "hfg_forward",
     "hfg_forward_stages", "hfg_forward_host", "hfg_last_launch_count",
+    "hfg_set_profiling", "hfg_get_profile",
 ]
 
 
@@ -84,6 +85,10 @@ def load():
     lib.hfg_forward_host.argtypes = [vp, vp, i32, i32, vp, i32]
     lib.hfg_last_launch_count.restype = ctypes.c_int
     lib.hfg_last_launch_count.argtypes = [vp, i64p]
+    lib.hfg_set_profiling.restype = ctypes.c_int
+    lib.hfg_set_profiling.argtypes = [vp, i32]
+    lib.hfg_get_profile.restype = ctypes.c_int
+    lib.hfg_get_profile.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     del fp
     _lib = lib
     return lib
@@ -172,6 +177,17 @@ class Handle:
 
     def forward_host(self, mel_ptr: int, batch: int, frames: int, wav_ptr: int, mode: int):
         self._check(self._lib.hfg_forward_host(self._h, mel_ptr, batch, frames, wav_ptr, mode))
+
+    def set_profiling(self, on: bool):
+        self._check(self._lib.hfg_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self):
+        import json
+        need = ctypes.c_size_t()
+        self._check(self._lib.hfg_get_profile(self._h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        self._check(self._lib.hfg_get_profile(self._h, buf, need.value, ctypes.byref(need)))
+        return json.loads(buf.value.decode())
 
     def last_launch_count(self) -> int:
         out = ctypes.c_int64()

@@ -51,7 +51,8 @@ template <int RCO>
 __global__ void __launch_bounds__(kThreads)
 conv_tile_fp32(const ConvArgs a) {
     constexpr int TCO = RCO * 16;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float fp32_smem[];
+    float* smem = fp32_smem;
 
     const int tx = threadIdx.x & 15;
     const int ty = threadIdx.x >> 4;

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -194,17 +195,23 @@ static void stage_geometry(const hfg_handle* h, int T, std::vector<int>& C, std:
 // fp32 launch plan
 // ---------------------------------------------------------------------------
 
-static void launch_conv_fp32(hfg_handle* h, cudaStream_t st, const ConvArgs& a, int rco, int nq, int B) {
+static void launch_conv_fp32(hfg_handle* h, cudaStream_t st, const ConvArgs& a, int rco, int nq, int B,
+                             const char* label) {
     const int tco = rco * 16;
+    // algorithmic work: 2*Cin*Cout*k per output step (Conv1d) / per input step (ConvTranspose1d)
+    const double flops = 2.0 * a.Cin * a.Cout * a.k * (double)B * (a.phases > 1 ? a.Tin : a.Tout);
+    const double bytes = 4.0 * B * ((double)a.Cin * a.Tin + (double)a.Cout * a.Tout * (a.res ? 2 : 1)) +
+                         4.0 * a.Cin * a.Cout * a.k;
     const int span = (a.taps_max - 1) * (a.dil < 0 ? -a.dil : a.dil);
     const size_t smem = sizeof(float) * ((size_t)kTileCi * (kTileT + span) + (size_t)a.taps_max * kTileCi * tco);
     dim3 grid((nq + kTileT - 1) / kTileT, a.phases * a.co_tiles, B);
+    h->prof_begin(st, label, flops, bytes);
     switch (rco) {
         case 8: conv_tile_fp32<8><<<grid, kThreads, smem, st>>>(a); break;
         case 4: conv_tile_fp32<4><<<grid, kThreads, smem, st>>>(a); break;
         default: conv_tile_fp32<2><<<grid, kThreads, smem, st>>>(a); break;
     }
-    h->launches++;
+    h->prof_end(st);
     check_cuda(cudaGetLastError(), "conv_tile_fp32 launch");
 }
 
@@ -243,7 +250,7 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
 
     // conv_pre (reference :238), no activation on the mel
     float* cur = bufA;
-    launch_conv_fp32(h, st, conv_args(h->pre, mel, cur, T, 1.0f), h->pre.rco, T, B);
+    launch_conv_fp32(h, st, conv_args(h->pre, mel, cur, T, 1.0f), h->pre.rco, T, B, "conv_pre");
     dump(0, cur, (size_t)B * C[0] * L[0]);
 
     for (size_t i = 0; i < h->ups.size(); ++i) {
@@ -259,7 +266,7 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
         a.co_tiles = U.cout_pad / (U.rco * 16);
         a.slope = slope; a.epi_flags = 0; a.div = 1.f;
         const int nq = (Tout - 1 + U.p) / U.u + 1;
-        launch_conv_fp32(h, st, a, U.rco, nq, B);
+        launch_conv_fp32(h, st, a, U.rco, nq, B, ("ups" + std::to_string(i)).c_str());
         const size_t n = (size_t)B * U.cout * Tout;
         dump(1 + 2 * (int)i, bufX, n);
 
@@ -270,14 +277,15 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
             const float* r = bufX;
             for (size_t l = 0; l < rb.size(); ++l) {
                 const bool last = (l + 1 == rb.size());
-                launch_conv_fp32(h, st, conv_args(rb[l].c1, r, bufH, Tout, slope), rb[l].c1.rco, Tout, B);
+                const std::string lab = "mrf" + std::to_string(i);
+                launch_conv_fp32(h, st, conv_args(rb[l].c1, r, bufH, Tout, slope), rb[l].c1.rco, Tout, B, lab.c_str());
                 ConvArgs a2 = conv_args(rb[l].c2, bufH, last ? acc : bufR, Tout, slope);
                 a2.res = r;
                 if (last) {
                     if (j > 0) a2.epi_flags |= EPI_ACC_READ;
                     if (j == n_rb - 1) { a2.epi_flags |= EPI_ACC_DIV; a2.div = (float)n_rb; }
                 }
-                launch_conv_fp32(h, st, a2, rb[l].c2.rco, Tout, B);
+                launch_conv_fp32(h, st, a2, rb[l].c2.rco, Tout, B, lab.c_str());
                 r = bufR;
             }
         }
@@ -289,8 +297,10 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
     p.x = cur; p.w = h->post_w; p.bias = h->post_b; p.y = wav;
     p.Cin = h->post_cin; p.T = (int)L.back(); p.k = 7; p.pad = 3; p.slope = slope;
     dim3 grid((p.T + 255) / 256, B);
+    h->prof_begin(st, "conv_post", 2.0 * p.Cin * p.k * (double)B * p.T,
+                  4.0 * B * ((double)p.Cin * p.T + p.T));
     conv_post_tanh_fp32<<<grid, 256, sizeof(float) * p.Cin * p.k, st>>>(p);
-    h->launches++;
+    h->prof_end(st);
     check_cuda(cudaGetLastError(), "conv_post launch");
 }
 
@@ -339,6 +349,8 @@ static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
     if (!ws || ws_bytes < need_bytes) throw StatusError(HFG_ERR_WORKSPACE, "workspace too small");
     if (((uintptr_t)ws & 255) != 0) throw StatusError(HFG_ERR_WORKSPACE, "workspace must be 256-byte aligned");
     h->launches = 0;
+    h->prof.clear();
+    h->events_used = 0;
     if (mode == HFG_MODE_FP32) forward_fp32(h, mel, B, T, wav, (char*)ws, st, stage_out);
     else tc_forward(h, mel, B, T, wav, (char*)ws, mode, st, stage_out);
 }
@@ -503,6 +515,40 @@ int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_
     check_cuda(cudaMemcpyAsync(h->pin_wav, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
     check_cuda(cudaStreamSynchronize(h->stream), "stream sync");
     memcpy(wav_host, h->pin_wav, wav_bytes);
+    HFG_CATCH(h)
+}
+
+int hfg_set_profiling(hfg_handle* h, int32_t enable) {
+    if (!h) return HFG_ERR_INVALID;
+    h->profiling = enable != 0;
+    return HFG_OK;
+}
+
+int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed) {
+    if (!h || !needed) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    // aggregate by label, in first-seen order
+    std::vector<std::string> order;
+    std::map<std::string, std::array<double, 4>> agg;   // launches, ms, flops, bytes
+    for (auto& r : h->prof) {
+        check_cuda(cudaEventSynchronize(r.e1), "cudaEventSynchronize");
+        float ms = 0.f;
+        check_cuda(cudaEventElapsedTime(&ms, r.e0, r.e1), "cudaEventElapsedTime");
+        if (!agg.count(r.label)) { order.push_back(r.label); agg[r.label] = {0, 0, 0, 0}; }
+        auto& a = agg[r.label];
+        a[0] += 1; a[1] += ms; a[2] += r.flops; a[3] += r.bytes;
+    }
+    std::string js = "[";
+    for (size_t i = 0; i < order.size(); ++i) {
+        const auto& a = agg[order[i]];
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s{\"kernel\":\"%s\",\"launches\":%d,\"ms\":%.6f,\"flops\":%.6e,\"bytes\":%.6e}",
+                 i ? "," : "", order[i].c_str(), (int)a[0], a[1], a[2], a[3]);
+        js += tmp;
+    }
+    js += "]";
+    *needed = js.size() + 1;
+    if (buf && buf_bytes >= js.size() + 1) memcpy(buf, js.c_str(), js.size() + 1);
     HFG_CATCH(h)
 }
 

@@ -82,6 +82,33 @@ struct hfg_handle {
 
     std::vector<void*> device_allocs;
 
+    // optional per-launch timing (hfg_set_profiling): one event pair per launch
+    struct ProfRec { std::string label; double flops; double bytes; cudaEvent_t e0, e1; };
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+    cudaEvent_t next_event() {
+        if (events_used == event_pool.size()) {
+            cudaEvent_t e;
+            hfg::check_cuda(cudaEventCreate(&e), "cudaEventCreate");
+            event_pool.push_back(e);
+        }
+        return event_pool[events_used++];
+    }
+    // call before / after a launch
+    void prof_begin(cudaStream_t st, const char* label, double flops, double bytes) {
+        launches++;
+        if (!profiling) return;
+        ProfRec r{label, flops, bytes, next_event(), next_event()};
+        hfg::check_cuda(cudaEventRecord(r.e0, st), "cudaEventRecord");
+        prof.push_back(r);
+    }
+    void prof_end(cudaStream_t st) {
+        if (!profiling) return;
+        hfg::check_cuda(cudaEventRecord(prof.back().e1, st), "cudaEventRecord");
+    }
+
     // hfg_forward_host resources
     cudaStream_t stream = nullptr;
     float* pin_mel = nullptr; size_t pin_mel_bytes = 0;

@@ -1,0 +1,476 @@
+// tcgen05 implicit-GEMM convolution for the HiFi-GAN generator (sm_100a).
+//
+// Data layout ("chunk planes").  An activation tensor with C channels and T time
+// steps is stored as  act[b][c / CW][PADL + t][c % CW]  where one (row, chunk)
+// cell is 16 bytes: CW = 8 channels in bf16 mode, 4 channels in tf32 mode (fp32
+// storage).  Each plane has TP rows; rows [0, PADL) and [PADL + T, TP) are kept
+// zero, which realises every layer's own zero padding (reference Conv1d
+// padding=..., models/hifigan.py:52-69) without any bounds logic in the loads.
+//
+// Why this layout: a [rows x 16 B] plane segment is exactly one column of UMMA
+// K-major *no-swizzle* core matrices (8 rows x 16 B, rows 16 B apart, SBO = 128 B).
+// A tile of R rows x 8 chunks therefore lands in shared memory with 8 plain 1-D
+// bulk copies (cp.async.bulk, no tensor map), and -- because row r sits at byte
+// r*16 of its chunk column -- the k taps of the convolution are the SAME smem
+// tile addressed with the descriptor start address shifted by tap*dilation rows.
+// No im2col, no re-load per tap.
+//
+//   D[128 x N] (TMEM, fp32) += A[128 x 16|8] (smem, shifted rows) * W_tap[N x 16|8]^T (smem)
+//
+//   M = time rows, N = output channels (<= 256 per CTA), K = input channels per tap.
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer, warp 1 = TMEM allocator +
+// single-thread MMA issuer, warps 2..5 = epilogue (one TMEM lane = one time row per
+// thread).  Rings: A stages (one per 8-chunk K block) and W stages (one per
+// (K block, tap)), full/empty mbarriers; tcgen05.commit releases stages.
+//
+// The epilogue fuses bias, the residual add (x recovered from the stored
+// leaky_relu(x) by the exact inverse), the MRF running sum / division, the NEXT
+// layer's leaky_relu (every conv output in this network is consumed through
+// leaky_relu(.,0.1): reference models/hifigan.py:81,83,244,254) and the
+// conversion to the operand dtype.  ConvTranspose1d runs as `phases` = u
+// polyphase convolutions whose outputs interleave with stride u.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hfg {
+
+constexpr int kTcThreads = 192;
+constexpr int kPadL = 32;          // zero rows in front of t = 0 in every plane
+constexpr int kMaxSA = 2, kMaxSW = 8;
+
+enum : int { TC_ACC_NONE = 0, TC_ACC_WRITE = 1, TC_ACC_ADD = 2, TC_ACC_FINAL = 3 };
+
+struct TcConvArgs {
+    // A operand: plane(b, chunk) = a + b*a_bstride + chunk*a_pstride; row r at +16 r
+    const uint8_t* a; long long a_bstride, a_pstride; int a_nchunks;
+    // packed weights: block(phase, ntile, kb, tap) of 8*N*16 bytes, [chunk][n][16 B]
+    const uint8_t* w; long long w_phase_stride, w_ntile_stride;
+    const float* bias;
+    // output / residual planes (operand dtype, chunk layout, same geometry)
+    uint8_t* out; const uint8_t* res; long long o_bstride, o_pstride;
+    // MRF accumulator planes: fp32, 4 channels per 16-byte cell
+    float* acc; long long acc_bstride, acc_pstride;   // in bytes
+    int acc_mode; float inv_scale;                    // TC_ACC_FINAL: v = (acc + v) / n_resblocks
+    float div;
+    int N;              // output channels handled by this CTA (multiple of 16, <= 256)
+    int MT;             // 128-row sub-tiles per CTA (MT * N <= 512 TMEM columns)
+    int n_q;            // number of q positions
+    int T_out;          // valid output rows
+    int taps_max, k, u, dil, pad, phases;
+    int out_stride, out_off;   // t = q*out_stride + phase + out_off
+    int min_off;        // smallest input row offset over taps
+    int R;              // rows per A stage = MT*128 + span
+    int sa, sw;         // ring depths
+    int tiles_per_batch;
+    float slope;        // leaky_relu slope fused on the OUTPUT (and inverted on the residual)
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must trap (-> CUDA error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    long long t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && (++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();     // ~2 s at 2 GHz
+        }
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleaved" core matrices):
+//   bits [0,14) start>>4, [16,30) LBO>>4 (stride between K-adjacent core matrices),
+//   [32,46) SBO>>4 (stride between 8-row groups), [46,48) version = 1, [61,64) layout = 0
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+           ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// UMMA instruction descriptor: fp32 accumulate, K-major A and B, M = 128
+template <bool BF16>
+__device__ __forceinline__ uint32_t umma_idesc(int N) {
+    const uint32_t fmt = BF16 ? 1u : 2u;            // 1 = BF16, 2 = TF32
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+__device__ __forceinline__ float lrelu_inv(float v, float inv_s) { return v > 0.f ? v : v * inv_s; }
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
+    lo = __uint_as_float(u << 16);
+    hi = __uint_as_float(u & 0xFFFF0000u);
+}
+
+// ------------------------------------------------------------------ the kernel
+template <bool BF16>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_kernel(const TcConvArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_smem[];
+    uint8_t* smem = tc_smem;
+    constexpr int CW = BF16 ? 8 : 4;       // channels per 16-byte cell
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, MT = a.MT, R = a.R;
+    const int nck_max = a.a_nchunks < 8 ? a.a_nchunks : 8;
+    const uint32_t a_stage_bytes = (uint32_t)R * nck_max * 16;
+    const uint32_t w_stage_bytes = (uint32_t)N * nck_max * 16;
+    uint8_t* sA = smem;
+    uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
+    float* sBias = reinterpret_cast<float*>(sW + (size_t)a.sw * w_stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + N);
+    // barrier slots: a_full[2] a_empty[2] w_full[8] w_empty[8] acc_full[1]
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](int i) { return bar0 + 8u * i; };
+    auto A_EMPTY = [&](int i) { return bar0 + 8u * (kMaxSA + i); };
+    auto W_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxSA + i); };
+    auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxSA + kMaxSW + i); };
+    const uint32_t ACC_FULL = bar0 + 8u * (2 * kMaxSA + 2 * kMaxSW);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 1);
+
+    // tile coordinates
+    const int b = blockIdx.x / a.tiles_per_batch;
+    const int q0 = (blockIdx.x % a.tiles_per_batch) * MT * 128;
+    const int n_tiles = gridDim.y / a.phases;
+    const int phase = blockIdx.y / n_tiles;
+    const int ntile = blockIdx.y % n_tiles;
+    int taps = a.taps_max;
+    if (a.phases > 1) taps = (a.k - phase + a.u - 1) / a.u;
+    const int n_chunks = a.a_nchunks;
+    const int n_kb = (n_chunks + 7) / 8;
+
+    uint32_t ncols = 32;
+    while ((int)ncols < MT * N) ncols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), 1); mbar_init(A_EMPTY(i), 1); }
+        for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), 1); mbar_init(W_EMPTY(i), 1); }
+        mbar_init(ACC_FULL, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < N; i += 128) sBias[i] = a.bias[ntile * N + i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: bulk copies =====================
+        if (lane == 0) {
+            const uint8_t* ab = a.a + (long long)b * a.a_bstride + (long long)(kPadL + q0 + a.min_off) * 16;
+            const uint8_t* wb = a.w + (long long)phase * a.w_phase_stride + (long long)ntile * a.w_ntile_stride;
+            int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+            auto issue_a = [&](int kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
+                mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R * 16);
+                const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
+                for (int c = 0; c < nck; ++c)
+                    bulk_g2s(dst + (uint32_t)c * R * 16, ab + (long long)(8 * kb + c) * a.a_pstride,
+                             (uint32_t)R * 16, A_FULL(sa_i));
+                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+            };
+            issue_a(0);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
+                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)nck * N * 16);
+                    bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
+                             wb + (long long)(kb * a.taps_max + tap) * (8ll * N * 16),
+                             (uint32_t)nck * N * 16, W_FULL(sw_i));
+                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                    if (tap == 0 && kb + 1 < n_kb) issue_a(kb + 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc<BF16>(N);
+            int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+            uint32_t first = 1;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                mbar_wait(A_FULL(sa_i), sa_ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
+                for (int tap = 0; tap < taps; ++tap) {
+                    mbar_wait(W_FULL(sw_i), sw_ph);
+                    tc_fence_after();
+                    const uint32_t w_addr = smem_u32(sW + (size_t)sw_i * w_stage_bytes);
+                    const int row_off = tap * a.dil - a.pad - a.min_off;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        for (int s = 0; s < nck / 2; ++s) {
+                            const uint64_t ad = umma_desc(a_addr + (uint32_t)((2 * s) * R + mt * 128 + row_off) * 16,
+                                                          (uint32_t)R * 16, 128);
+                            const uint64_t bd = umma_desc(w_addr + (uint32_t)(2 * s) * N * 16, (uint32_t)N * 16, 128);
+                            umma<BF16>(tmem_base + (uint32_t)(mt * N), ad, bd, idesc,
+                                       (first && s == 0) ? 0u : 1u);
+                        }
+                    }
+                    first = 0;
+                    tc_commit(W_EMPTY(sw_i));
+                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                }
+                tc_commit(A_EMPTY(sa_i));
+                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+            }
+            tc_commit(ACC_FULL);
+        }
+    } else {
+        // ===================== epilogue: TMEM -> regs -> global =====================
+        mbar_wait(ACC_FULL, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+        const int qlane = quarter * 32 + lane;
+        const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        for (int mt = 0; mt < MT; ++mt) {
+            const int q = q0 + mt * 128 + qlane;
+            const int t = q * a.out_stride + phase + a.out_off;
+            const bool valid = (q < a.n_q) && (t >= 0) && (t < a.T_out);
+            const long long row_bytes = (long long)(kPadL + t) * 16;
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * N + c0), r);
+                tmem_ld_wait();
+                if (!valid) continue;
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[c0 + i];
+                const int ch0 = ntile * N + c0;             // first output channel of this group
+                if (a.res) {                                 // x + xt   (reference :85)
+                    const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
+                    if constexpr (BF16) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(rp + (long long)(ch0 / CW + g) * a.o_pstride);
+                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float lo, hi;
+                                unpack_bf16(w4[i], lo, hi);
+                                v[g * 8 + 2 * i] += lrelu_inv(lo, inv_slope);
+                                v[g * 8 + 2 * i + 1] += lrelu_inv(hi, inv_slope);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 u = *reinterpret_cast<const float4*>(rp + (long long)(ch0 / CW + g) * a.o_pstride);
+                            v[g * 4 + 0] += lrelu_inv(u.x, inv_slope);
+                            v[g * 4 + 1] += lrelu_inv(u.y, inv_slope);
+                            v[g * 4 + 2] += lrelu_inv(u.z, inv_slope);
+                            v[g * 4 + 3] += lrelu_inv(u.w, inv_slope);
+                        }
+                    }
+                }
+                if (a.acc_mode != TC_ACC_NONE) {             // MRF sum (reference :126-131)
+                    uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float4* cell = reinterpret_cast<float4*>(ap + (long long)(ch0 / 4 + g) * a.acc_pstride);
+                        if (a.acc_mode != TC_ACC_WRITE) {
+                            const float4 u = *cell;
+                            v[g * 4 + 0] += u.x; v[g * 4 + 1] += u.y; v[g * 4 + 2] += u.z; v[g * 4 + 3] += u.w;
+                        }
+                        if (a.acc_mode != TC_ACC_FINAL)
+                            *cell = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                    if (a.acc_mode == TC_ACC_FINAL) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
+                    }
+                }
+                if (a.out) {                                 // next layer's leaky_relu, operand dtype
+                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                    if constexpr (BF16) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint4 u;
+                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                            u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                            u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                            *reinterpret_cast<uint4*>(op + (long long)(ch0 / CW + g) * a.o_pstride) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<float4*>(op + (long long)(ch0 / CW + g) * a.o_pstride) =
+                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ small helpers
+// mel [B, C, T] fp32 (reference layout) -> chunk planes in the operand dtype (no activation).
+template <bool BF16>
+__global__ void tc_pack_input(const float* __restrict__ x, uint8_t* __restrict__ out, int C, int T,
+                              long long bstride, long long pstride) {
+    constexpr int CW = BF16 ? 8 : 4;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    float v[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = x[((size_t)b * C + chunk * CW + i) * T + t];
+    uint8_t* p = out + (long long)b * bstride + (long long)chunk * pstride + (long long)(kPadL + t) * 16;
+    if constexpr (BF16) {
+        uint4 u;
+        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
+        u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p) = u;
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// chunk planes holding leaky_relu(x) -> x as [B, C, T] fp32 (stage dumps for tests).
+template <bool BF16>
+__global__ void tc_unpack_stage(const uint8_t* __restrict__ in, float* __restrict__ y, int C, int T,
+                                long long bstride, long long pstride, float inv_slope) {
+    constexpr int CW = BF16 ? 8 : 4;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const uint8_t* p = in + (long long)b * bstride + (long long)chunk * pstride + (long long)(kPadL + t) * 16;
+    float v[CW];
+    if constexpr (BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
+        unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
+    } else {
+        const float4 u = *reinterpret_cast<const float4*>(p);
+        v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i)
+        y[((size_t)b * C + chunk * CW + i) * T + t] = lrelu_inv(v[i], inv_slope);
+}
+
+// Zero the padding rows [0, PADL) and [PADL + T, TP) of every plane of up to 40 buffers.
+struct PadJob { uint8_t* base; long long planes; int TP; int T; };
+struct PadJobs { PadJob job[40]; int n; };
+__global__ void tc_zero_pads(const PadJobs jobs) {
+    const PadJob j = jobs.job[blockIdx.y];
+    const int pad_rows = j.TP - j.T;                       // front PADL rows + tail rows
+    const long long total = j.planes * pad_rows;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long plane = e / pad_rows;
+        int r = (int)(e - plane * pad_rows);
+        if (r >= kPadL) r += j.T;                          // skip the valid rows
+        *reinterpret_cast<uint4*>(j.base + (plane * j.TP + r) * 16) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// conv_post (C_out = 1, k taps) + tanh from chunk planes that already hold leaky_relu(x)
+// (reference models/hifigan.py:254-256).  One thread per output sample; bandwidth kernel.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ y, int C, int T, int k, int pad, long long bstride, long long pstride) {
+    constexpr int CW = BF16 ? 8 : 4;
+    extern __shared__ float wsm[];                          // [k][C]
+    for (int e = threadIdx.x; e < C * k; e += blockDim.x) {
+        const int ci = e / k, j = e - ci * k;
+        wsm[j * C + ci] = w[e];                             // w is [C][k]
+    }
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const uint8_t* base = in + (long long)b * bstride + (long long)(kPadL + t - pad) * 16;
+    float acc = 0.f;
+    for (int chunk = 0; chunk < C / CW; ++chunk) {
+        const uint8_t* p = base + (long long)chunk * pstride;
+        for (int j = 0; j < k; ++j) {
+            float v[CW];
+            if constexpr (BF16) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p + j * 16);
+                unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
+                unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
+            } else {
+                const float4 u = *reinterpret_cast<const float4*>(p + j * 16);
+                v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+            }
+            const float* wr = wsm + j * C + chunk * CW;
+#pragma unroll
+            for (int i = 0; i < CW; ++i) acc = fmaf(wr[i], v[i], acc);
+        }
+    }
+    y[(size_t)b * T + t] = tanhf(acc + bias[0]);
+}
+
+}  // namespace hfg
