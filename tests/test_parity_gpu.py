@@ -187,3 +187,40 @@ def test_c_abi_error_codes():
     torch.cuda.synchronize()
     assert h.last_launch_count() > 0
     h.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_time_chunking_with_halo_equals_unchunked(mode):
+    """BASELINE.json configs[3]: one 60 s mel (5168 frames) cut into 8 chunks with
+    a 14-frame halo reproduces the unchunked run (size-independent property; the
+    per-output accumulation order does not depend on the tile position, so the
+    match is bit-exact)."""
+    from tts_sambert_hifigan_b200 import sharding
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 4), mode)
+    mel = torch.from_numpy(synth.make_mel(9, 1, 80, 5168)).to("cuda:0")
+    with torch.no_grad():
+        full = gen(mel)
+        got = sharding.generate_chunked(gen, mel, 8, hop=256, halo=14)
+        bad = sharding.generate_chunked(gen, mel, 8, hop=256, halo=5)
+    torch.cuda.synchronize()
+    assert got.shape == full.shape == (1, 1, 5168 * 256)
+    err = float((got - full).abs().max())
+    print(f"chunked-vs-full[{mode}] {err:.3e}; halo=5 err {float((bad - full).abs().max()):.3e}")
+    assert err == 0.0
+    assert float((bad - full).abs().max()) > 1e-6     # the halo is doing real work
+
+
+def test_long_form_against_oracle():
+    """Largest single-utterance size the suite runs against the CPU oracle."""
+    import oracle
+    cfg = synth.DEFAULT_CONFIG
+    sd = synth.make_weights(cfg, 4)
+    mel = synth.make_mel(9, 1, 80, 1024)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()},
+                               torch.from_numpy(mel)).numpy()
+    for mode in ("tf32", "bf16"):
+        wav = run(make_gen(cfg, sd, mode), mel)
+        err = float(np.abs(wav - ref).max())
+        print(f"long-form[{mode}] max-abs {err:.3e}")
+        assert err <= TOL[mode]

@@ -101,6 +101,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -213,70 +223,88 @@ tc_conv_kernel(const TcConvArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Roles are warp-uniform: the whole warp runs the loop nest (so loop counters and
+    // descriptors stay in uniform registers) and one elected lane issues the async ops.
     if (warp == 0) {
         // ===================== producer: bulk copies =====================
-        if (lane == 0) {
-            const uint8_t* ab = a.a + (long long)b * a.a_bstride + (long long)(kPadL + q0 + a.min_off) * 16;
-            const uint8_t* wb = a.w + (long long)phase * a.w_phase_stride + (long long)ntile * a.w_ntile_stride;
-            int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
-            auto issue_a = [&](int kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
-                mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
+        const bool leader = elect_one();
+        const uint8_t* ab = a.a + (long long)b * a.a_bstride + (long long)(kPadL + q0 + a.min_off) * 16;
+        const uint8_t* wb = a.w + (long long)phase * a.w_phase_stride + (long long)ntile * a.w_ntile_stride;
+        int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+        auto issue_a = [&](int kb) {
+            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
+            if (leader) {
                 mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R * 16);
                 const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
                 for (int c = 0; c < nck; ++c)
                     bulk_g2s(dst + (uint32_t)c * R * 16, ab + (long long)(8 * kb + c) * a.a_pstride,
                              (uint32_t)R * 16, A_FULL(sa_i));
-                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
-            };
-            issue_a(0);
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
-                for (int tap = 0; tap < taps; ++tap) {
-                    mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
+            }
+            __syncwarp();
+            if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+        };
+        issue_a(0);
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
+                if (leader) {
                     mbar_expect_tx(W_FULL(sw_i), (uint32_t)nck * N * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
                              wb + (long long)(kb * a.taps_max + tap) * (8ll * N * 16),
                              (uint32_t)nck * N * 16, W_FULL(sw_i));
-                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                    if (tap == 0 && kb + 1 < n_kb) issue_a(kb + 1);
                 }
+                __syncwarp();
+                if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                if (tap == 0 && kb + 1 < n_kb) issue_a(kb + 1);
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc<BF16>(N);
-            int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
-            uint32_t first = 1;
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
-                mbar_wait(A_FULL(sa_i), sa_ph);
+        // ===================== MMA issuer (one elected lane) =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc<BF16>(N);
+        // descriptor high words are loop-invariant; the low word is start>>4 | LBO>>4 << 16,
+        // so stepping K chunks / sub-tiles / taps is an add of (bytes >> 4) = rows on the low word
+        const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;        // SBO = 128 B, version 1
+        const uint32_t a_lbo = ((uint32_t)R) << 16, b_lbo = ((uint32_t)N) << 16;
+        int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+        uint32_t acc_on = 0;
+        for (int kb = 0; kb < n_kb; ++kb) {
+            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            const int ksteps = nck >> 1;
+            mbar_wait(A_FULL(sa_i), sa_ph);
+            tc_fence_after();
+            const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+            for (int tap = 0; tap < taps; ++tap) {
+                mbar_wait(W_FULL(sw_i), sw_ph);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
-                for (int tap = 0; tap < taps; ++tap) {
-                    mbar_wait(W_FULL(sw_i), sw_ph);
-                    tc_fence_after();
-                    const uint32_t w_addr = smem_u32(sW + (size_t)sw_i * w_stage_bytes);
-                    const int row_off = tap * a.dil - a.pad - a.min_off;
+                const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                const uint32_t a_lo1 = a_lo0 + (uint32_t)(tap * a.dil - a.pad - a.min_off);
+                if (leader) {
                     for (int mt = 0; mt < MT; ++mt) {
-                        for (int s = 0; s < nck / 2; ++s) {
-                            const uint64_t ad = umma_desc(a_addr + (uint32_t)((2 * s) * R + mt * 128 + row_off) * 16,
-                                                          (uint32_t)R * 16, 128);
-                            const uint64_t bd = umma_desc(w_addr + (uint32_t)(2 * s) * N * 16, (uint32_t)N * 16, 128);
-                            umma<BF16>(tmem_base + (uint32_t)(mt * N), ad, bd, idesc,
-                                       (first && s == 0) ? 0u : 1u);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(mt * N);
+                        uint32_t a_lo = a_lo1 + (uint32_t)(mt * 128), b_lo = b_lo0;
+#pragma unroll 4
+                        for (int s = 0; s < ksteps; ++s) {
+                            umma<BF16>(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
+                                       acc_on | (uint32_t)s);
+                            a_lo += 2u * (uint32_t)R;
+                            b_lo += 2u * (uint32_t)N;
                         }
                     }
-                    first = 0;
                     tc_commit(W_EMPTY(sw_i));
-                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                 }
-                tc_commit(A_EMPTY(sa_i));
-                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+                __syncwarp();
+                acc_on = 1;
+                if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
             }
-            tc_commit(ACC_FULL);
+            if (leader) tc_commit(A_EMPTY(sa_i));
+            __syncwarp();
+            if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
         }
+        if (leader) tc_commit(ACC_FULL);
+        __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> regs -> global =====================
         mbar_wait(ACC_FULL, 0);
