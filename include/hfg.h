@@ -128,6 +128,14 @@ int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_
 int hfg_set_profiling(hfg_handle* h, int32_t enable);
 int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed);
 
+/* Tuning / profiling aid: time `iters` launches of ONE MRF convolution
+ * (mrfs[stage].resblocks[resblock].convs{1,2}[pair]; which = 0 / 1, or 2 for the
+ * fused conv1+conv2 pair kernel) of the
+ * tensor-core path on scratch buffers of `batch` x `rows` time steps.
+ * Returns the average milliseconds per launch. */
+int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair, int32_t which,
+                    int32_t batch, int32_t rows, int32_t mode, int32_t iters, float* ms);
+
 /* Number of kernels the last hfg_forward* call on this handle launched. */
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches);
 

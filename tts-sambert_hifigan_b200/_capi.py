@@ -16,7 +16,7 @@ SYMBOLS = [
     "hfg_abi_version", "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_weight",
     "hfg_commit_weights", "hfg_out_len", "hfg_workspace_bytes", "hfg_forward",
     "hfg_forward_stages", "hfg_forward_host", "hfg_last_launch_count",
-    "hfg_set_profiling", "hfg_get_profile",
+    "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer",
 ]
 
 
@@ -89,6 +89,8 @@ def load():
     lib.hfg_set_profiling.argtypes = [vp, i32]
     lib.hfg_get_profile.restype = ctypes.c_int
     lib.hfg_get_profile.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.hfg_bench_layer.restype = ctypes.c_int
+    lib.hfg_bench_layer.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, fp]
     del fp
     _lib = lib
     return lib
@@ -188,6 +190,12 @@ class Handle:
         buf = ctypes.create_string_buffer(need.value)
         self._check(self._lib.hfg_get_profile(self._h, buf, need.value, ctypes.byref(need)))
         return json.loads(buf.value.decode())
+
+    def bench_layer(self, stage, resblock, pair, which, batch, rows, mode, iters=20) -> float:
+        ms = ctypes.c_float()
+        self._check(self._lib.hfg_bench_layer(self._h, stage, resblock, pair, which, batch, rows, mode, iters,
+                                              ctypes.byref(ms)))
+        return ms.value
 
     def last_launch_count(self) -> int:
         out = ctypes.c_int64()

@@ -552,6 +552,22 @@ int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed) 
     HFG_CATCH(h)
 }
 
+int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair, int32_t which,
+                    int32_t batch, int32_t rows, int32_t mode, int32_t iters, float* ms) {
+    if (!h || !ms) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
+    if (!tc_supported(h)) throw StatusError(HFG_ERR_UNSUPPORTED, "tensor-core path unsupported for this config");
+    if (stage < 0 || stage >= (int)h->mrfs.size() || resblock < 0 || resblock >= (int)h->mrfs[stage].size() ||
+        pair < 0 || pair >= (int)h->mrfs[stage][resblock].size() || which < 0 || which > 2 || batch <= 0 ||
+        rows <= 0 || iters <= 0)
+        throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: bad argument");
+    if (mode == HFG_MODE_BF16) *ms = tc_bench_layer_impl<true>(h, stage, resblock, pair, which, batch, rows, iters);
+    else if (mode == HFG_MODE_TF32) *ms = tc_bench_layer_impl<false>(h, stage, resblock, pair, which, batch, rows, iters);
+    else throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: tensor-core modes only");
+    HFG_CATCH(h)
+}
+
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches) {
     if (!h || !launches) return HFG_ERR_INVALID;
     *launches = h->launches;

@@ -1,0 +1,398 @@
+// Fused ResBlock pair on tcgen05 (sm_100a):
+//
+//     x_new = x + conv2( leaky_relu( conv1_d( leaky_relu(x) ) + b1 ) ) + b2
+//                                             (reference models/hifigan.py:80-85)
+//
+// in ONE persistent kernel: the intermediate never leaves the SM, the residual is
+// never re-read from global memory, and both leaky_relus, both biases, the
+// residual add, the MRF running sum / division (reference :126-131) and the
+// conversion to the operand dtype are fused.
+//
+// Per tile (one utterance, TO = MT*128 - (k-1) output time steps):
+//
+//   producer warp   bulk-copies the leaky_relu(x) tile (rows t0-p2-p1 .. , 8-chunk K blocks)
+//                   and streams W1 then W2 (one (K block, tap) stage at a time)
+//   MMA warp        conv1: D1[mt] += A(shifted by tap*d rows) * W1[tap]      (acc1, TMEM)
+//                   conv2: D2[mt] += H(shifted by tap rows)   * W2[tap]      (acc2, TMEM)
+//   8 epilogue warps
+//     pre2  (overlaps conv1 MMAs)  acc2 <- x + b2 (+ MRF partial sum): the residual is the
+//           centre rows of the A tile already in smem (leaky_relu inverted exactly), written
+//           to TMEM with tcgen05.st, so conv2 simply accumulates on top of it
+//     epi1  acc1 -> +b1 -> leaky_relu -> zero outside [0,T) (conv2's own zero padding)
+//           -> operand dtype -> smem H tile in the same chunk-plane layout conv2's A
+//           descriptors address with row shifts
+//     epi2  acc2 -> (MRF sum bookkeeping) -> leaky_relu for the next consumer -> global
+//
+// TMEM: acc1 = MT*N columns, acc2 = MT*N columns (MT*N <= 256).  While the epilogue
+// warps drain acc2 of tile i the MMA warp already runs conv1 of tile i+1 into acc1.
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace hfg {
+
+constexpr int kPairEpiWarps = 8;
+constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+
+struct TcPairArgs {
+    const uint8_t* a; long long a_bstride, a_pstride;     // leaky_relu(x) planes
+    const uint8_t* w1; const uint8_t* w2;                 // packed [kb][tap][8][N][16 B]
+    const float* b1; const float* b2;
+    uint8_t* out; long long o_bstride, o_pstride;         // leaky_relu(x_new) planes (may be null)
+    float* acc; long long acc_bstride, acc_pstride;       // MRF fp32 partial sums (bytes)
+    int acc_mode; float div;
+    int N;            // channels (C_in = C_out = N)
+    int n_chunks;     // N / CW
+    int MT;           // 128-row sub-tiles per tile
+    int T;            // valid time steps
+    int k, dil, p1, p2;
+    int R1;           // rows per A stage   = MT*128 + 2*p1
+    int RH;           // rows per H plane  >= MT*128 + 2*p2
+    int TO;           // output rows per tile = MT*128 - 2*p2
+    int sa, sw;
+    int tiles_per_batch, n_tiles;
+    float slope;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                   "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                   "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPairThreads, 1)
+tc_pair_kernel(const TcPairArgs a) {
+    extern __shared__ __align__(128) uint8_t tc_pair_smem[];
+    uint8_t* smem = tc_pair_smem;
+    constexpr int CW = BF16 ? 8 : 4;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = a.N, MT = a.MT, R1 = a.R1, RH = a.RH, k = a.k;
+    const int n_chunks = a.n_chunks;
+    const int nck_max = n_chunks < 8 ? n_chunks : 8;
+    const int n_kb = (n_chunks + 7) / 8;
+    const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
+    const uint32_t w_stage_bytes = (uint32_t)N * nck_max * 16;
+    uint8_t* sA = smem;
+    uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
+    uint8_t* sH = sW + (size_t)a.sw * w_stage_bytes;
+    float* sB1 = reinterpret_cast<float*>(sH + (size_t)n_chunks * RH * 16);
+    float* sB2 = sB1 + N;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + N);
+    const uint32_t bar0 = smem_u32(bars);
+    auto A_FULL = [&](int i) { return bar0 + 8u * i; };
+    auto A_EMPTY = [&](int i) { return bar0 + 8u * (kMaxSA + i); };
+    auto W_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxSA + i); };
+    auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxSA + kMaxSW + i); };
+    const uint32_t ACC1_FULL = bar0 + 8u * (2 * kMaxSA + 2 * kMaxSW);
+    const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 3);
+
+    uint32_t ncols = 32;
+    while ((int)ncols < 2 * MT * N) ncols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), 1); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
+        for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), 1); mbar_init(W_EMPTY(i), 1); }
+        mbar_init(ACC1_FULL, 1);
+        mbar_init(H_READY, kPairEpiWarps);
+        mbar_init(ACC2_FULL, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < N; i += 32 * kPairEpiWarps) { sB1[i] = a.b1[i]; sB2[i] = a.b2[i]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc1 = tmem_base, acc2 = tmem_base + (uint32_t)(MT * N);
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        const bool leader = elect_one();
+        int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+        auto tile_src = [&](int tile) {
+            const int b = tile / a.tiles_per_batch;
+            const int t0 = (tile % a.tiles_per_batch) * a.TO;
+            return a.a + (long long)b * a.a_bstride + (long long)(kPadL + t0 - a.p2 - a.p1) * 16;
+        };
+        auto issue_a = [&](const uint8_t* ab, int kb) {
+            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
+            if (leader) {
+                mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
+                const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
+                for (int c = 0; c < nck; ++c)
+                    bulk_g2s(dst + (uint32_t)c * R1 * 16, ab + (long long)(8 * kb + c) * a.a_pstride,
+                             (uint32_t)R1 * 16, A_FULL(sa_i));
+            }
+            __syncwarp();
+            if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+        };
+        auto issue_w = [&](const uint8_t* w, int kb, int tap) {
+            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
+            if (leader) {
+                mbar_expect_tx(W_FULL(sw_i), (uint32_t)nck * N * 16);
+                bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
+                         w + (long long)(kb * k + tap) * (8ll * N * 16), (uint32_t)nck * N * 16, W_FULL(sw_i));
+            }
+            __syncwarp();
+            if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+        };
+        if ((int)blockIdx.x < a.n_tiles) issue_a(tile_src(blockIdx.x), 0);
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const uint8_t* ab = tile_src(tile);
+            const int next = tile + (int)gridDim.x;
+            for (int kb = 0; kb < n_kb; ++kb)
+                for (int tap = 0; tap < k; ++tap) {
+                    issue_w(a.w1, kb, tap);
+                    if (tap == 0 && kb + 1 < n_kb) issue_a(ab, kb + 1);
+                }
+            for (int kb = 0; kb < n_kb; ++kb)
+                for (int tap = 0; tap < k; ++tap) {
+                    issue_w(a.w2, kb, tap);
+                    // first K block of the NEXT tile: lands while conv2 of this tile still runs
+                    if (kb == 0 && tap == 0 && next < a.n_tiles) issue_a(tile_src(next), 0);
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const bool leader = elect_one();
+        const uint32_t idesc = umma_idesc<BF16>(N);
+        const uint32_t d_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
+        const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)N) << 16;
+        const uint32_t h_lo_base = ((smem_u32(sH) & 0x3FFFFu) >> 4) | h_lbo;
+        int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1 ----
+            uint32_t acc_on = 0;
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                const int ksteps = nck >> 1;
+                mbar_wait(A_FULL(sa_i), sa_ph);
+                tc_fence_after();
+                const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+                for (int tap = 0; tap < k; ++tap) {
+                    mbar_wait(W_FULL(sw_i), sw_ph);
+                    tc_fence_after();
+                    const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    if (leader) {
+                        for (int mt = 0; mt < MT; ++mt) {
+                            uint32_t a_lo = a_lo0 + (uint32_t)(tap * a.dil + mt * 128), b_lo = b_lo0;
+#pragma unroll 4
+                            for (int s = 0; s < ksteps; ++s) {
+                                umma<BF16>(acc1 + (uint32_t)(mt * N), ((uint64_t)d_hi << 32) | a_lo,
+                                           ((uint64_t)d_hi << 32) | b_lo, idesc, acc_on | (uint32_t)s);
+                                a_lo += 2u * (uint32_t)R1;
+                                b_lo += 2u * (uint32_t)N;
+                            }
+                        }
+                        tc_commit(W_EMPTY(sw_i));
+                    }
+                    __syncwarp();
+                    acc_on = 1;
+                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                }
+                if (leader) tc_commit(A_EMPTY(sa_i));
+                __syncwarp();
+                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+            }
+            if (leader) tc_commit(ACC1_FULL);
+            __syncwarp();
+            // ---- conv2: acc2 (pre-loaded with x + b2) += sum_{kb,tap} H(+tap rows) * W2 ----
+            mbar_wait(H_READY, it & 1);
+            tc_fence_after();
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                const int ksteps = nck >> 1;
+                const uint32_t h_lo0 = h_lo_base + (uint32_t)(8 * kb * RH);
+                for (int tap = 0; tap < k; ++tap) {
+                    mbar_wait(W_FULL(sw_i), sw_ph);
+                    tc_fence_after();
+                    const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    if (leader) {
+                        for (int mt = 0; mt < MT; ++mt) {
+                            uint32_t h_lo = h_lo0 + (uint32_t)(tap + mt * 128), b_lo = b_lo0;
+#pragma unroll 4
+                            for (int s = 0; s < ksteps; ++s) {
+                                umma<BF16>(acc2 + (uint32_t)(mt * N), ((uint64_t)d_hi << 32) | h_lo,
+                                           ((uint64_t)d_hi << 32) | b_lo, idesc, 1u);
+                                h_lo += 2u * (uint32_t)RH;
+                                b_lo += 2u * (uint32_t)N;
+                            }
+                        }
+                        tc_commit(W_EMPTY(sw_i));
+                    }
+                    __syncwarp();
+                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                }
+            }
+            if (leader) tc_commit(ACC2_FULL);
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int half = e >> 2;                      // the two warps of a quarter split the sub-tiles
+        const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
+        const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
+        const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        int sa_i = 0, sa_ph = 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_batch;
+            const int t0 = (tile % a.tiles_per_batch) * a.TO;
+            // ---------- pre2: acc2 <- x + b2 (+ partial MRF sum), per K block as it lands ----------
+            for (int kb = 0; kb < n_kb; ++kb) {
+                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                mbar_wait(A_FULL(sa_i), sa_ph);
+                const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
+                for (int mt = half; mt < MT; mt += 2) {
+                    const int lr = mt * 128 + row;                      // output row inside the tile
+                    const int t = t0 + lr;
+                    const bool valid = lr < a.TO && t < a.T;
+                    const uint8_t* rp = sa_p + (size_t)(lr + a.p2 + a.p1) * 16;
+                    const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
+                                          (long long)(kPadL + t) * 16;
+                    const bool add_prev = valid && (a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL);
+                    for (int c8 = 0; c8 < nck * CW; c8 += 8) {           // 8 columns at a time
+                        const int col = kb * 8 * CW + c8;
+                        float v[8];
+                        if constexpr (BF16) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(rp + (size_t)(c8 / 8) * R1 * 16);
+                            unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
+                            unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
+                        } else {
+                            const float4 u0 = *reinterpret_cast<const float4*>(rp + (size_t)(c8 / 4) * R1 * 16);
+                            const float4 u1 = *reinterpret_cast<const float4*>(rp + (size_t)(c8 / 4 + 1) * R1 * 16);
+                            v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+                            v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = lrelu_inv(v[i], inv_slope) + sB2[col + i];
+                        if (add_prev) {
+                            const float4 p0 = *reinterpret_cast<const float4*>(accp + (long long)(col / 4) * a.acc_pstride);
+                            const float4 p1 = *reinterpret_cast<const float4*>(accp + (long long)(col / 4 + 1) * a.acc_pstride);
+                            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
+                            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+                        }
+                        tmem_st8(acc2 + lane_sel + (uint32_t)(mt * N + col), v);
+                    }
+                }
+                tmem_st_wait();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(A_EMPTY(sa_i));
+                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+            }
+            // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
+            mbar_wait(ACC1_FULL, it & 1);
+            tc_fence_after();
+            for (int mt = half; mt < MT; mt += 2) {
+                const int hr = mt * 128 + row;                          // H row inside the tile
+                const int th = t0 - a.p2 + hr;                          // its time step
+                const bool hvalid = th >= 0 && th < a.T;
+                uint8_t* hp = sH + (size_t)hr * 16;
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(acc1 + lane_sel + (uint32_t)(mt * N + c0), r);
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float x = lrelu(__uint_as_float(r[i]) + sB1[c0 + i], slope);
+                        v[i] = hvalid ? x : 0.f;                        // conv2 zero-pads ITS input
+                    }
+                    if constexpr (BF16) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint4 u;
+                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                            *reinterpret_cast<uint4*>(hp + (size_t)(c0 / 8 + g) * RH * 16) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<float4*>(hp + (size_t)(c0 / 4 + g) * RH * 16) =
+                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                }
+            }
+            fence_async_smem();          // H (generic-proxy writes) must be visible to the MMA (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(H_READY);
+            // ---------- epi2: acc2 -> global ----------
+            mbar_wait(ACC2_FULL, it & 1);
+            tc_fence_after();
+            for (int mt = half; mt < MT; mt += 2) {
+                const int lr = mt * 128 + row;
+                const int t = t0 + lr;
+                const bool valid = lr < a.TO && t < a.T;
+                const long long row_bytes = (long long)(kPadL + t) * 16;
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(acc2 + lane_sel + (uint32_t)(mt * N + c0), r);
+                    tmem_ld_wait();
+                    if (!valid) continue;
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+                    if (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD) {
+                        uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<float4*>(ap + (long long)(c0 / 4 + g) * a.acc_pstride) =
+                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        continue;
+                    }
+                    if (a.acc_mode == TC_ACC_FINAL) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
+                    }
+                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                    if constexpr (BF16) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint4 u;
+                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                            *reinterpret_cast<uint4*>(op + (long long)(c0 / CW + g) * a.o_pstride) = u;
+                        }
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            *reinterpret_cast<float4*>(op + (long long)(c0 / CW + g) * a.o_pstride) =
+                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    }
+                }
+            }
+            tc_fence_before();           // order these TMEM reads before the next tile's tcgen05.st / MMA
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace hfg

@@ -8,6 +8,7 @@
 #include "fp32_kernels.cuh"
 #include "model.h"
 #include "tc_kernels.cuh"
+#include "tc_pair_kernel.cuh"
 
 namespace hfg {
 
@@ -120,9 +121,9 @@ struct TcPlane {            // geometry of one activation tensor in chunk-plane 
     size_t off = 0;
 };
 
-// rows per plane: PADL zero rows, the data rounded up so that every tile (<= 512 rows, plus up to
-// 32 polyphase/halo rows) stays inside the plane, and 32 trailing zero rows
-static inline int tc_tp(long long T) { return kPadL + (int)((T + 32 + 511) / 512 * 512) + 32; }
+// rows per plane: PADL zero rows, the data, and enough trailing zero rows that a tile (<= 512 rows)
+// starting anywhere below T, plus its halo / polyphase overhang (<= 32 + 25 rows), stays inside
+static inline int tc_tp(long long T) { return kPadL + (int)((T + 127) / 128 * 128) + 512 + 64; }
 
 static inline TcPlane tc_plane(int B, int C, long long T, int cw, size_t& cursor) {
     TcPlane p;
@@ -208,6 +209,70 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     tc_conv_kernel<BF16><<<grid, kTcThreads, smem, st>>>(a);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_conv_kernel launch");
+}
+
+// ---- fused ResBlock pair ----
+struct PairGeom { int MT, sa, sw, R1, RH, TO; size_t smem; int occ; bool ok; };
+
+static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks) {
+    PairGeom g{};
+    const int N = P.c1.cout, k = P.c1.k, p1 = P.c1.pad, p2 = P.c2.pad;
+    g.ok = false;
+    if (env_int("HFG_TC_FUSE", 1) == 0) return g;
+    if (N > env_int("HFG_TC_FUSE_MAXC", 256) || N % 16 != 0 || P.c1.cin != N || P.c2.cin != N || P.c2.cout != N) return g;
+    if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
+    const int nck_max = std::min(8, n_chunks), n_kb = (n_chunks + 7) / 8;
+    const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
+    for (int MT : {4, 2, 1}) {
+        if (MT > mt_cap || 2 * MT * N > 512) continue;
+        for (int sw : {4, 3, 2}) {
+            const int sa = std::min(kMaxSA, n_kb);
+            const int R1 = MT * 128 + 2 * p1;
+            const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
+            const size_t smem = (size_t)sa * R1 * nck_max * 16 + (size_t)sw * N * nck_max * 16 +
+                                (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 256;
+            if (smem > (size_t)kTcSmemLimit) continue;
+            g.MT = MT; g.sa = sa; g.sw = sw; g.R1 = R1; g.RH = RH; g.TO = MT * 128 - 2 * p2; g.smem = smem;
+            int ncols = 32;
+            while (ncols < 2 * MT * N) ncols <<= 1;
+            g.occ = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 512 / ncols));
+            g.ok = true;
+            (void)k; (void)h;
+            return g;
+        }
+    }
+    return g;
+}
+
+template <bool BF16>
+static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, const PairGeom& g,
+                           const uint8_t* in, long long in_b, long long in_p, int n_chunks,
+                           uint8_t* out, long long out_b, long long out_p,
+                           float* acc, long long acc_b, long long acc_p, int acc_mode, float div,
+                           int B, int T, const char* label) {
+    constexpr int ESZ = BF16 ? 2 : 4;
+    TcPairArgs a{};
+    a.a = in; a.a_bstride = in_b; a.a_pstride = in_p;
+    a.w1 = reinterpret_cast<const uint8_t*>(BF16 ? P.c1.tc.w_bf16 : P.c1.tc.w_tf32);
+    a.w2 = reinterpret_cast<const uint8_t*>(BF16 ? P.c2.tc.w_bf16 : P.c2.tc.w_tf32);
+    a.b1 = P.c1.bias; a.b2 = P.c2.bias;
+    a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
+    a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
+    a.N = P.c1.cout; a.n_chunks = n_chunks; a.MT = g.MT; a.T = T;
+    a.k = P.c1.k; a.dil = P.c1.dil; a.p1 = P.c1.pad; a.p2 = P.c2.pad;
+    a.R1 = g.R1; a.RH = g.RH; a.TO = g.TO; a.sa = g.sa; a.sw = g.sw;
+    a.tiles_per_batch = (T + g.TO - 1) / g.TO;
+    a.n_tiles = a.tiles_per_batch * B;
+    a.slope = 0.1f;
+    const int grid = std::min(a.n_tiles, h->sm_count * g.occ);
+    const double C = a.N;
+    const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
+    const double bytes = (double)B * T * C * ESZ * (out ? 2 : 1) +
+                         (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
+    h->prof_begin(st, label, flops, bytes);
+    tc_pair_kernel<BF16><<<grid, kPairThreads, g.smem, st>>>(a);
+    h->prof_end(st);
+    check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
 }
 
 template <bool BF16>
@@ -314,19 +379,26 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             const TcPlane* r = &S.X;
             for (size_t l = 0; l < rb.size(); ++l) {
                 const bool last = (l + 1 == rb.size());
-                conv(rb[l].c1, *r, &S.H, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
-                if (!last) {
-                    conv(rb[l].c2, S.H, &S.R, r, nullptr, TC_ACC_NONE, lab.c_str());
+                int mode = TC_ACC_NONE;
+                if (last && n_rb > 1) mode = j == 0 ? TC_ACC_WRITE : (j == n_rb - 1 ? TC_ACC_FINAL : TC_ACC_ADD);
+                // destination of this pair: ping-pong between R and H; the last pair feeds the MRF sum / Y
+                const TcPlane* dst = last ? ((mode == TC_ACC_WRITE || mode == TC_ACC_ADD) ? nullptr : &S.Y)
+                                          : (r == &S.R ? &S.H : &S.R);
+                const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks);
+                if (g.ok) {
+                    tc_launch_pair<BF16>(h, st, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
+                                         dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
+                                         mode != TC_ACC_NONE ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
+                                         S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb, B, S.X.T, lab.c_str());
                 } else {
-                    int mode = n_rb == 1 ? TC_ACC_FINAL : (j == 0 ? TC_ACC_WRITE : (j == n_rb - 1 ? TC_ACC_FINAL : TC_ACC_ADD));
-                    if (n_rb == 1) {
-                        // single resblock: no accumulator traffic, just divide
-                        conv(rb[l].c2, S.H, &S.Y, r, nullptr, TC_ACC_NONE, lab.c_str());
-                    } else {
-                        conv(rb[l].c2, S.H, mode == TC_ACC_FINAL ? &S.Y : nullptr, r, &S.ACC, mode, lab.c_str());
-                    }
+                    // unfused fallback: conv1 -> T (scratch), conv2 (+ residual) -> dst
+                    const TcPlane* scratch = nullptr;
+                    for (const TcPlane* c : {&S.H, &S.R, &S.Y})
+                        if (c != r && c != dst) { scratch = c; break; }
+                    conv(rb[l].c1, *r, scratch, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
+                    conv(rb[l].c2, *scratch, dst, r, mode != TC_ACC_NONE ? &S.ACC : nullptr, mode, lab.c_str());
                 }
-                r = &S.R;
+                if (!last) r = dst;
             }
         }
         cur = &S.Y;
@@ -346,6 +418,59 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     (void)CW;
 }
 
+// Micro-benchmark of ONE MRF convolution launch on scratch planes (tuning / ncu).
+// which: 0 = convs1[pair], 1 = convs2[pair] (with residual).  Returns avg ms per launch.
+template <bool BF16>
+static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pair, int which, int B, int T, int iters) {
+    constexpr int ESZ = BF16 ? 2 : 4;
+    const PairLayers& P = h->mrfs.at(stage).at(resblock).at(pair);
+    const ConvLayer& L = which == 1 ? P.c2 : P.c1;
+    size_t cur = 0;
+    const int cw = BF16 ? 8 : 4;
+    TcPlane in = tc_plane(B, L.cin, T, cw, cur), out = tc_plane(B, L.cout, T, cw, cur), res = tc_plane(B, L.cout, T, cw, cur);
+    char* ws = nullptr;
+    check_cuda(cudaMalloc((void**)&ws, cur), "cudaMalloc(bench)");
+    check_cuda(cudaMemset(ws, 0, cur), "cudaMemset(bench)");
+    cudaStream_t st = 0;
+    TcConvArgs a{};
+    a.a = (uint8_t*)ws + in.off; a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
+    a.N = tc_pick_n(L.cout);
+    a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
+    a.w_ntile_stride = (long long)((in.nchunks + 7) / 8) * L.k * 8 * a.N * 16;
+    a.bias = L.bias;
+    a.out = (uint8_t*)ws + out.off; a.res = which ? (uint8_t*)ws + res.off : nullptr;
+    a.o_bstride = out.bstride; a.o_pstride = out.pstride;
+    a.acc_mode = TC_ACC_NONE; a.div = 1.f;
+    a.n_q = T; a.T_out = T; a.taps_max = L.k; a.k = L.k; a.u = 1; a.dil = L.dil; a.pad = L.pad; a.phases = 1;
+    a.out_stride = 1; a.out_off = 0; a.min_off = -L.pad; a.slope = 0.1f;
+    const bool was = h->profiling;
+    h->profiling = false;
+    cudaEvent_t e0, e1;
+    check_cuda(cudaEventCreate(&e0), "event"); check_cuda(cudaEventCreate(&e1), "event");
+    const PairGeom g = tc_pair_geometry(h, P, in.nchunks);
+    if (which == 2 && !g.ok) throw StatusError(HFG_ERR_UNSUPPORTED, "fused pair does not fit for this layer");
+    auto launch = [&]() {
+        if (which == 2)
+            tc_launch_pair<BF16>(h, st, P, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
+                                 (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
+                                 B, T, "bench");
+        else
+            tc_launch_conv<BF16>(h, st, a, B, L.cout, "bench", 0, 0);
+    };
+    for (int i = 0; i < 3; ++i) launch();
+    check_cuda(cudaEventRecord(e0, st), "record");
+    for (int i = 0; i < iters; ++i) launch();
+    check_cuda(cudaEventRecord(e1, st), "record");
+    check_cuda(cudaEventSynchronize(e1), "sync");
+    float ms = 0.f;
+    check_cuda(cudaEventElapsedTime(&ms, e0, e1), "elapsed");
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(ws);
+    h->profiling = was;
+    (void)ESZ;
+    return ms / iters;
+}
+
 inline void tc_forward(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws, int mode,
                        cudaStream_t st, float* const* stage_out) {
     if (h->cc_major != 10)
@@ -361,6 +486,8 @@ inline void configure_kernels(hfg_handle*) {
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
 }
 
 }  // namespace hfg
