@@ -40,7 +40,9 @@ class HfgError(RuntimeError):
         self.code = code
 
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libhfg_b200.so")
+# HFG_LIB_PATH: A/B-test another build of the same ABI (kernel tuning only)
+_LIB_PATH = os.environ.get("HFG_LIB_PATH") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "lib", "libhfg_b200.so")
 _lib = None
 
 

@@ -46,7 +46,8 @@ enum : int { TC_ACC_NONE = 0, TC_ACC_WRITE = 1, TC_ACC_ADD = 2, TC_ACC_FINAL = 3
 struct TcConvArgs {
     // A operand: plane(b, chunk) = a + b*a_bstride + chunk*a_pstride; row r at +16 r
     const uint8_t* a; long long a_bstride, a_pstride; int a_nchunks;
-    // packed weights: block(phase, ntile, kb, tap) of 8*N*16 bytes, [chunk][n][16 B]
+    // packed weights, tight: block(kb, tap) = [nck(kb) chunks][N][16 B]; taps of a K block are contiguous:
+    //   offset(kb, tap) = (kb*taps_max*8 + tap*nck(kb)) * N * 16
     const uint8_t* w; long long w_phase_stride, w_ntile_stride;
     const float* bias;
     // output / residual planes (operand dtype, chunk layout, same geometry)
@@ -64,6 +65,7 @@ struct TcConvArgs {
     int min_off;        // smallest input row offset over taps
     int R;              // rows per A stage = MT*128 + span
     int sa, sw;         // ring depths
+    int tap_group;      // taps per W stage (small layers: fewer, fatter stages)
     int tiles_per_batch;
     float slope;        // leaky_relu slope fused on the OUTPUT (and inverted on the residual)
 };
@@ -143,6 +145,26 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
+// One (tap, sub-tile): `ksteps` K-steps of UMMA_K (two 16-byte cells each), A and B descriptors
+// advanced by 2 cells per step.  The common 4-step case is straight-line code so the
+// UTCHMMAs issue back to back from uniform registers.
+template <bool BF16>
+__device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo,
+                                            uint32_t a_step, uint32_t b_step, uint32_t idesc, int ksteps,
+                                            uint32_t acc_first) {
+    if (ksteps == 4) {
+        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first);
+        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + a_step), ((uint64_t)hi << 32) | (b_lo + b_step), idesc, 1u);
+        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 2 * a_step), ((uint64_t)hi << 32) | (b_lo + 2 * b_step), idesc, 1u);
+        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 3 * a_step), ((uint64_t)hi << 32) | (b_lo + 3 * b_step), idesc, 1u);
+    } else {
+        for (int s = 0; s < ksteps; ++s) {
+            umma<BF16>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first | (uint32_t)s);
+            a_lo += a_step;
+            b_lo += b_step;
+        }
+    }
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -150,10 +172,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+          "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+          "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15])) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float lrelu(float v, float s) { return v > 0.f ? v : v * s; }
-__device__ __forceinline__ float lrelu_inv(float v, float inv_s) { return v > 0.f ? v : v * inv_s; }
+// leaky_relu with 0 < s < 1 is max(v, s v); its inverse (1/s > 1) is min(v, v/s): two instructions each
+__device__ __forceinline__ float lrelu(float v, float s) { return fmaxf(v, v * s); }
+__device__ __forceinline__ float lrelu_inv(float v, float inv_s) { return fminf(v, v * inv_s); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -162,6 +194,63 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
     lo = __uint_as_float(u << 16);
     hi = __uint_as_float(u & 0xFFFF0000u);
+}
+
+// 16 consecutive channels of one row <-> 16-byte cells of consecutive chunk planes
+template <bool BF16>
+__device__ __forceinline__ void store_cells16(uint8_t* p, long long plane_stride, const float (&v)[16]) {
+    if constexpr (BF16) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            uint4 u;
+            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(p + g * plane_stride) = u;
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(p + g * plane_stride) =
+                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    }
+}
+template <bool BF16>
+__device__ __forceinline__ void load_cells16(const uint8_t* p, long long plane_stride, float (&v)[16]) {
+    if constexpr (BF16) {
+        uint4 u[2];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) u[g] = *reinterpret_cast<const uint4*>(p + g * plane_stride);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            unpack_bf16(u[g].x, v[g * 8 + 0], v[g * 8 + 1]); unpack_bf16(u[g].y, v[g * 8 + 2], v[g * 8 + 3]);
+            unpack_bf16(u[g].z, v[g * 8 + 4], v[g * 8 + 5]); unpack_bf16(u[g].w, v[g * 8 + 6], v[g * 8 + 7]);
+        }
+    } else {
+        float4 u[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) u[g] = *reinterpret_cast<const float4*>(p + g * plane_stride);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { v[g * 4 + 0] = u[g].x; v[g * 4 + 1] = u[g].y; v[g * 4 + 2] = u[g].z; v[g * 4 + 3] = u[g].w; }
+    }
+}
+__device__ __forceinline__ void load_f32x16(const uint8_t* p, long long plane_stride, float (&v)[16]) {
+    float4 u[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) u[g] = *reinterpret_cast<const float4*>(p + g * plane_stride);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { v[g * 4 + 0] = u[g].x; v[g * 4 + 1] = u[g].y; v[g * 4 + 2] = u[g].z; v[g * 4 + 3] = u[g].w; }
+}
+__device__ __forceinline__ void store_f32x16(uint8_t* p, long long plane_stride, const float (&v)[16]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(p + g * plane_stride) = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+}
+__device__ __forceinline__ void add_bias16(float (&v)[16], const float* sb) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(sb + 4 * g);
+        v[g * 4 + 0] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -176,7 +265,8 @@ tc_conv_kernel(const TcConvArgs a) {
     const int N = a.N, MT = a.MT, R = a.R;
     const int nck_max = a.a_nchunks < 8 ? a.a_nchunks : 8;
     const uint32_t a_stage_bytes = (uint32_t)R * nck_max * 16;
-    const uint32_t w_stage_bytes = (uint32_t)N * nck_max * 16;
+    const int G = a.tap_group;
+    const uint32_t w_stage_bytes = (uint32_t)G * N * nck_max * 16;
     uint8_t* sA = smem;
     uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
     float* sBias = reinterpret_cast<float*>(sW + (size_t)a.sw * w_stage_bytes);
@@ -247,17 +337,18 @@ tc_conv_kernel(const TcConvArgs a) {
         issue_a(0);
         for (int kb = 0; kb < n_kb; ++kb) {
             const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap0 = 0; tap0 < taps; tap0 += G) {
+                const int g = (taps - tap0) < G ? (taps - tap0) : G;
                 mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
                 if (leader) {
-                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)nck * N * 16);
+                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * N * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
-                             wb + (long long)(kb * a.taps_max + tap) * (8ll * N * 16),
-                             (uint32_t)nck * N * 16, W_FULL(sw_i));
+                             wb + ((long long)kb * a.taps_max * 8 + (long long)tap0 * nck) * N * 16,
+                             (uint32_t)g * nck * N * 16, W_FULL(sw_i));
                 }
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                if (tap == 0 && kb + 1 < n_kb) issue_a(kb + 1);
+                if (tap0 == 0 && kb + 1 < n_kb) issue_a(kb + 1);
             }
         }
     } else if (warp == 1) {
@@ -276,22 +367,18 @@ tc_conv_kernel(const TcConvArgs a) {
             mbar_wait(A_FULL(sa_i), sa_ph);
             tc_fence_after();
             const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
-            for (int tap = 0; tap < taps; ++tap) {
+            for (int tap0 = 0; tap0 < taps; tap0 += G) {
+                const int g = (taps - tap0) < G ? (taps - tap0) : G;
                 mbar_wait(W_FULL(sw_i), sw_ph);
                 tc_fence_after();
-                const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                const uint32_t a_lo1 = a_lo0 + (uint32_t)(tap * a.dil - a.pad - a.min_off);
+                const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                 if (leader) {
-                    for (int mt = 0; mt < MT; ++mt) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(mt * N);
-                        uint32_t a_lo = a_lo1 + (uint32_t)(mt * 128), b_lo = b_lo0;
-#pragma unroll 4
-                        for (int s = 0; s < ksteps; ++s) {
-                            umma<BF16>(d_tmem, ((uint64_t)a_hi << 32) | a_lo, ((uint64_t)b_hi << 32) | b_lo, idesc,
-                                       acc_on | (uint32_t)s);
-                            a_lo += 2u * (uint32_t)R;
-                            b_lo += 2u * (uint32_t)N;
-                        }
+                    for (int tt = 0; tt < g; ++tt) {
+                        const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
+                        const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil - a.pad - a.min_off);
+                        for (int mt = 0; mt < MT; ++mt)
+                            umma_ksteps<BF16>(tmem_base + (uint32_t)(mt * N), a_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                              2u * (uint32_t)R, 2u * (uint32_t)N, idesc, ksteps, acc_on | (uint32_t)tt);
                     }
                     tc_commit(W_EMPTY(sw_i));
                 }

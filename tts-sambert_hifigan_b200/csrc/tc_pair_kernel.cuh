@@ -49,6 +49,7 @@ struct TcPairArgs {
     int RH;           // rows per H plane  >= MT*128 + 2*p2
     int TO;           // output rows per tile = MT*128 - 2*p2
     int sa, sw;
+    int tap_group;    // taps per W stage
     int tiles_per_batch, n_tiles;
     float slope;
 };
@@ -65,8 +66,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool BF16>
-__global__ void __launch_bounds__(kPairThreads, 1)
+// MINB = CTAs per SM the register allocation must allow (2 for the narrow layers, whose tiles are
+// latency-bound and want a second CTA to fill the tensor pipe while the first one is in an epilogue)
+template <bool BF16, int MINB>
+__global__ void __launch_bounds__(kPairThreads, MINB)
 tc_pair_kernel(const TcPairArgs a) {
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
     uint8_t* smem = tc_pair_smem;
@@ -78,7 +81,8 @@ tc_pair_kernel(const TcPairArgs a) {
     const int nck_max = n_chunks < 8 ? n_chunks : 8;
     const int n_kb = (n_chunks + 7) / 8;
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
-    const uint32_t w_stage_bytes = (uint32_t)N * nck_max * 16;
+    const int G = a.tap_group;
+    const uint32_t w_stage_bytes = (uint32_t)G * N * nck_max * 16;
     uint8_t* sA = smem;
     uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
     uint8_t* sH = sW + (size_t)a.sw * w_stage_bytes;
@@ -141,13 +145,15 @@ tc_pair_kernel(const TcPairArgs a) {
             __syncwarp();
             if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
         };
-        auto issue_w = [&](const uint8_t* w, int kb, int tap) {
+        auto issue_w = [&](const uint8_t* w, int kb, int tap0) {      // taps [tap0, tap0 + G) of K block kb
             const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            const int g = (k - tap0) < G ? (k - tap0) : G;
             mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
             if (leader) {
-                mbar_expect_tx(W_FULL(sw_i), (uint32_t)nck * N * 16);
+                mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * N * 16);
                 bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
-                         w + (long long)(kb * k + tap) * (8ll * N * 16), (uint32_t)nck * N * 16, W_FULL(sw_i));
+                         w + ((long long)kb * k * 8 + (long long)tap0 * nck) * N * 16, (uint32_t)g * nck * N * 16,
+                         W_FULL(sw_i));
             }
             __syncwarp();
             if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
@@ -157,12 +163,12 @@ tc_pair_kernel(const TcPairArgs a) {
             const uint8_t* ab = tile_src(tile);
             const int next = tile + (int)gridDim.x;
             for (int kb = 0; kb < n_kb; ++kb)
-                for (int tap = 0; tap < k; ++tap) {
+                for (int tap = 0; tap < k; tap += G) {
                     issue_w(a.w1, kb, tap);
                     if (tap == 0 && kb + 1 < n_kb) issue_a(ab, kb + 1);
                 }
             for (int kb = 0; kb < n_kb; ++kb)
-                for (int tap = 0; tap < k; ++tap) {
+                for (int tap = 0; tap < k; tap += G) {
                     issue_w(a.w2, kb, tap);
                     // first K block of the NEXT tile: lands while conv2 of this tile still runs
                     if (kb == 0 && tap == 0 && next < a.n_tiles) issue_a(tile_src(next), 0);
@@ -186,20 +192,19 @@ tc_pair_kernel(const TcPairArgs a) {
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
-                for (int tap = 0; tap < k; ++tap) {
+                for (int tap0 = 0; tap0 < k; tap0 += G) {
+                    const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
                     tc_fence_after();
-                    const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int mt = 0; mt < MT; ++mt) {
-                            uint32_t a_lo = a_lo0 + (uint32_t)(tap * a.dil + mt * 128), b_lo = b_lo0;
-#pragma unroll 4
-                            for (int s = 0; s < ksteps; ++s) {
-                                umma<BF16>(acc1 + (uint32_t)(mt * N), ((uint64_t)d_hi << 32) | a_lo,
-                                           ((uint64_t)d_hi << 32) | b_lo, idesc, acc_on | (uint32_t)s);
-                                a_lo += 2u * (uint32_t)R1;
-                                b_lo += 2u * (uint32_t)N;
-                            }
+                        for (int tt = 0; tt < g; ++tt) {
+                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
+                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil);
+                            for (int mt = 0; mt < MT; ++mt)
+                                umma_ksteps<BF16>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                  2u * (uint32_t)R1, 2u * (uint32_t)N, idesc, ksteps,
+                                                  acc_on | (uint32_t)tt);
                         }
                         tc_commit(W_EMPTY(sw_i));
                     }
@@ -220,20 +225,18 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
                 const int ksteps = nck >> 1;
                 const uint32_t h_lo0 = h_lo_base + (uint32_t)(8 * kb * RH);
-                for (int tap = 0; tap < k; ++tap) {
+                for (int tap0 = 0; tap0 < k; tap0 += G) {
+                    const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
                     tc_fence_after();
-                    const uint32_t b_lo0 = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int mt = 0; mt < MT; ++mt) {
-                            uint32_t h_lo = h_lo0 + (uint32_t)(tap + mt * 128), b_lo = b_lo0;
-#pragma unroll 4
-                            for (int s = 0; s < ksteps; ++s) {
-                                umma<BF16>(acc2 + (uint32_t)(mt * N), ((uint64_t)d_hi << 32) | h_lo,
-                                           ((uint64_t)d_hi << 32) | b_lo, idesc, 1u);
-                                h_lo += 2u * (uint32_t)RH;
-                                b_lo += 2u * (uint32_t)N;
-                            }
+                        for (int tt = 0; tt < g; ++tt) {
+                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
+                            const uint32_t h_lo1 = h_lo0 + (uint32_t)(tap0 + tt);
+                            for (int mt = 0; mt < MT; ++mt)
+                                umma_ksteps<BF16>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                  2u * (uint32_t)RH, 2u * (uint32_t)N, idesc, ksteps, 1u);
                         }
                         tc_commit(W_EMPTY(sw_i));
                     }
@@ -252,6 +255,9 @@ tc_pair_kernel(const TcPairArgs a) {
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        const long long a_plane = (long long)R1 * 16, h_plane = (long long)RH * 16;
+        const bool add_prev_mode = (a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL);
+        const bool acc_store_mode = (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD);
         int sa_i = 0, sa_ph = 0;
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -265,33 +271,25 @@ tc_pair_kernel(const TcPairArgs a) {
                 for (int mt = half; mt < MT; mt += 2) {
                     const int lr = mt * 128 + row;                      // output row inside the tile
                     const int t = t0 + lr;
-                    const bool valid = lr < a.TO && t < a.T;
+                    const bool add_prev = add_prev_mode && lr < a.TO && t < a.T;
                     const uint8_t* rp = sa_p + (size_t)(lr + a.p2 + a.p1) * 16;
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
-                    const bool add_prev = valid && (a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL);
-                    for (int c8 = 0; c8 < nck * CW; c8 += 8) {           // 8 columns at a time
-                        const int col = kb * 8 * CW + c8;
-                        float v[8];
-                        if constexpr (BF16) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(rp + (size_t)(c8 / 8) * R1 * 16);
-                            unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
-                            unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
-                        } else {
-                            const float4 u0 = *reinterpret_cast<const float4*>(rp + (size_t)(c8 / 4) * R1 * 16);
-                            const float4 u1 = *reinterpret_cast<const float4*>(rp + (size_t)(c8 / 4 + 1) * R1 * 16);
-                            v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
-                            v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
-                        }
+                    const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * 8 * CW);
+                    for (int c16 = 0; c16 < nck * CW; c16 += 16) {       // 16 columns at a time
+                        const int col = kb * 8 * CW + c16;
+                        float v[16];
+                        load_cells16<BF16>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
+                        float prev[16];
+                        if (add_prev) load_f32x16(accp + (long long)(col / 4) * a.acc_pstride, a.acc_pstride, prev);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = lrelu_inv(v[i], inv_slope) + sB2[col + i];
+                        for (int i = 0; i < 16; ++i) v[i] = lrelu_inv(v[i], inv_slope);
+                        add_bias16(v, sB2 + col);
                         if (add_prev) {
-                            const float4 p0 = *reinterpret_cast<const float4*>(accp + (long long)(col / 4) * a.acc_pstride);
-                            const float4 p1 = *reinterpret_cast<const float4*>(accp + (long long)(col / 4 + 1) * a.acc_pstride);
-                            v[0] += p0.x; v[1] += p0.y; v[2] += p0.z; v[3] += p0.w;
-                            v[4] += p1.x; v[5] += p1.y; v[6] += p1.z; v[7] += p1.w;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += prev[i];
                         }
-                        tmem_st8(acc2 + lane_sel + (uint32_t)(mt * N + col), v);
+                        tmem_st16(tbase + (uint32_t)c16, v);
                     }
                 }
                 tmem_st_wait();
@@ -305,31 +303,29 @@ tc_pair_kernel(const TcPairArgs a) {
             for (int mt = half; mt < MT; mt += 2) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
-                const bool hvalid = th >= 0 && th < a.T;
+                const float keep = (th >= 0 && th < a.T) ? 1.f : 0.f;   // conv2 zero-pads ITS input
                 uint8_t* hp = sH + (size_t)hr * 16;
-                for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(acc1 + lane_sel + (uint32_t)(mt * N + c0), r);
+                const uint32_t tbase = acc1 + lane_sel + (uint32_t)(mt * N);
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    const bool two = c0 + 16 < N;
+                    tmem_ld16(tbase + (uint32_t)c0, r0);
+                    if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
                     tmem_ld_wait();
                     float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x = lrelu(__uint_as_float(r[i]) + sB1[c0 + i], slope);
-                        v[i] = hvalid ? x : 0.f;                        // conv2 zero-pads ITS input
-                    }
-                    if constexpr (BF16) {
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
+                    add_bias16(v, sB1 + c0);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint4 u;
-                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                            *reinterpret_cast<uint4*>(hp + (size_t)(c0 / 8 + g) * RH * 16) = u;
-                        }
-                    } else {
+                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope) * keep;
+                    store_cells16<BF16>(hp + (long long)(c0 / CW) * h_plane, h_plane, v);
+                    if (two) {
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<float4*>(hp + (size_t)(c0 / 4 + g) * RH * 16) =
-                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
+                        add_bias16(v, sB1 + c0 + 16);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope) * keep;
+                        store_cells16<BF16>(hp + (long long)((c0 + 16) / CW) * h_plane, h_plane, v);
                     }
                 }
             }
@@ -345,42 +341,34 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int t = t0 + lr;
                 const bool valid = lr < a.TO && t < a.T;
                 const long long row_bytes = (long long)(kPadL + t) * 16;
-                for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(acc2 + lane_sel + (uint32_t)(mt * N + c0), r);
+                const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N);
+                uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+                uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                for (int c0 = 0; c0 < N; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    const bool two = c0 + 16 < N;
+                    tmem_ld16(tbase + (uint32_t)c0, r0);
+                    if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
                     tmem_ld_wait();
                     if (!valid) continue;
-                    float v[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-                    if (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD) {
-                        uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+                    for (int hh = 0; hh < 2; ++hh) {
+                        if (hh == 1 && !two) break;
+                        const int cc = c0 + 16 * hh;
+                        float v[16];
 #pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<float4*>(ap + (long long)(c0 / 4 + g) * a.acc_pstride) =
-                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                        continue;
-                    }
-                    if (a.acc_mode == TC_ACC_FINAL) {
+                        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(hh ? r1[i] : r0[i]);
+                        if (acc_store_mode) {
+                            store_f32x16(ap + (long long)(cc / 4) * a.acc_pstride, a.acc_pstride, v);
+                        } else {
+                            if (a.acc_mode == TC_ACC_FINAL) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
-                    }
-                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                                for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
+                            }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                    if constexpr (BF16) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint4 u;
-                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                            *reinterpret_cast<uint4*>(op + (long long)(c0 / CW + g) * a.o_pstride) = u;
+                            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                            store_cells16<BF16>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
                         }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<float4*>(op + (long long)(c0 / CW + g) * a.o_pstride) =
-                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
                     }
                 }
             }

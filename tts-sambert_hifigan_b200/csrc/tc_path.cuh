@@ -54,15 +54,17 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
     for (int bf = 0; bf < 2; ++bf) {
         const int CW = bf ? 8 : 4;
         const int nchunks = cin / CW, nkb = (nchunks + 7) / 8;
-        const size_t block = (size_t)8 * N * 16;                       // bytes per (kb, tap)
-        const size_t total = (size_t)phases * ntiles * nkb * taps_max * block;
+        // tight layout: [phase][ntile][kb][tap][chunk < nck(kb)][n][cell]
+        const size_t per_tile = (size_t)nchunks * N * 16 * taps_max;
+        const size_t total = (size_t)phases * ntiles * per_tile;
         std::vector<uint8_t> buf(total, 0);
         for (int ph = 0; ph < phases; ++ph)
             for (int nt = 0; nt < ntiles; ++nt)
-                for (int kb = 0; kb < nkb; ++kb)
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int nck = std::min(8, nchunks - 8 * kb);
                     for (int tap = 0; tap < taps_max; ++tap) {
-                        uint8_t* blk = buf.data() + ((((size_t)ph * ntiles + nt) * nkb + kb) * taps_max + tap) * block;
-                        const int nck = std::min(8, nchunks - 8 * kb);
+                        uint8_t* blk = buf.data() + ((size_t)ph * ntiles + nt) * per_tile +
+                                       ((size_t)kb * taps_max * 8 + (size_t)tap * nck) * N * 16;
                         for (int c = 0; c < nck; ++c)
                             for (int n = 0; n < N; ++n) {
                                 uint8_t* cell = blk + ((size_t)c * N + n) * 16;
@@ -79,6 +81,7 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
                                 }
                             }
                     }
+                }
         void* d = h->upload(buf);
         if (bf) tp.w_bf16 = d; else tp.w_tf32 = d;
     }
@@ -179,6 +182,13 @@ static inline int env_int(const char* name, int dflt) {
     return s ? atoi(s) : dflt;
 }
 
+// taps per W stage: aim at >= 16 KB per bulk copy so tiny layers do not drown in barrier round trips
+static inline int tc_tap_group(int N, int nck_max, int taps) {
+    const int tap_bytes = N * nck_max * 16;
+    const int g = std::max(1, env_int("HFG_TC_STAGE_BYTES", 16384) / tap_bytes);
+    return std::min(g, taps);
+}
+
 template <bool BF16>
 static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, int cout, const char* label,
                            double flops, double bytes) {
@@ -190,9 +200,11 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     MT = std::min(MT, env_int("HFG_TC_MT", 4));
     MT = std::max(1, std::min(MT, (a.n_q + 127) / 128));
     int sa = std::min(kMaxSA, n_kb), sw = std::min(kMaxSW, std::max(2, env_int("HFG_TC_SW", 4)));
+    const int G = tc_tap_group(a.N, nck_max, a.taps_max);
+    a.tap_group = G;
     auto smem_need = [&](int mt, int sa_, int sw_) {
         const size_t R = (size_t)mt * 128 + span;
-        return (size_t)sa_ * R * nck_max * 16 + (size_t)sw_ * a.N * nck_max * 16 + (size_t)a.N * 4 + 256;
+        return (size_t)sa_ * R * nck_max * 16 + (size_t)sw_ * G * a.N * nck_max * 16 + (size_t)a.N * 4 + 256;
     };
     while (smem_need(MT, sa, sw) > (size_t)kTcSmemLimit) {
         if (sw > 3) --sw;
@@ -212,7 +224,7 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
 }
 
 // ---- fused ResBlock pair ----
-struct PairGeom { int MT, sa, sw, R1, RH, TO; size_t smem; int occ; bool ok; };
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO; size_t smem; int occ; bool ok; };
 
 static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks) {
     PairGeom g{};
@@ -223,25 +235,35 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
     const int nck_max = std::min(8, n_chunks), n_kb = (n_chunks + 7) / 8;
     const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
+    // Candidates from the largest tile down.  Measured rule (profiles/r1_tuning.md): two co-resident
+    // CTAs per SM beat one CTA with a larger tile (one CTA's epilogue hides behind the other's MMAs),
+    // so take the largest MT that still allows 2 CTAs/SM, else the largest MT that fits.
+    PairGeom best{};
+    best.ok = false;
     for (int MT : {4, 2, 1}) {
         if (MT > mt_cap || 2 * MT * N > 512) continue;
         for (int sw : {4, 3, 2}) {
+            const int G = tc_tap_group(N, nck_max, k);
+            if (G > 1 && sw > 2) continue;                                // fat stages: two are enough
             const int sa = std::min(kMaxSA, n_kb);
             const int R1 = MT * 128 + 2 * p1;
             const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
-            const size_t smem = (size_t)sa * R1 * nck_max * 16 + (size_t)sw * N * nck_max * 16 +
+            const size_t smem = (size_t)sa * R1 * nck_max * 16 + (size_t)sw * G * N * nck_max * 16 +
                                 (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 256;
             if (smem > (size_t)kTcSmemLimit) continue;
-            g.MT = MT; g.sa = sa; g.sw = sw; g.R1 = R1; g.RH = RH; g.TO = MT * 128 - 2 * p2; g.smem = smem;
+            PairGeom c{};
+            c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2; c.smem = smem;
             int ncols = 32;
             while (ncols < 2 * MT * N) ncols <<= 1;
-            g.occ = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 512 / ncols));
-            g.ok = true;
-            (void)k; (void)h;
-            return g;
+            c.occ = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 512 / ncols));
+            c.ok = true;
+            if (!best.ok || (best.occ < 2 && c.occ >= 2)) best = c;
+            break;                                                        // deepest W ring that fits this MT
         }
+        if (best.ok && best.occ >= 2) break;
     }
-    return g;
+    (void)h;
+    return best;
 }
 
 template <bool BF16>
@@ -260,17 +282,31 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
     a.N = P.c1.cout; a.n_chunks = n_chunks; a.MT = g.MT; a.T = T;
     a.k = P.c1.k; a.dil = P.c1.dil; a.p1 = P.c1.pad; a.p2 = P.c2.pad;
-    a.R1 = g.R1; a.RH = g.RH; a.TO = g.TO; a.sa = g.sa; a.sw = g.sw;
+    a.R1 = g.R1; a.RH = g.RH; a.TO = g.TO; a.sa = g.sa; a.sw = g.sw; a.tap_group = g.G;
     a.tiles_per_batch = (T + g.TO - 1) / g.TO;
     a.n_tiles = a.tiles_per_batch * B;
     a.slope = 0.1f;
-    const int grid = std::min(a.n_tiles, h->sm_count * g.occ);
+    // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
+    // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
+    const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
+    static int regs_cache[2][2] = {{0, 0}, {0, 0}};
+    int& regs = regs_cache[BF16 ? 1 : 0][two ? 1 : 0];
+    if (regs == 0) {
+        cudaFuncAttributes fa{};
+        if (two) check_cuda(cudaFuncGetAttributes(&fa, tc_pair_kernel<BF16, 2>), "cudaFuncGetAttributes");
+        else check_cuda(cudaFuncGetAttributes(&fa, tc_pair_kernel<BF16, 1>), "cudaFuncGetAttributes");
+        regs = std::max(1, fa.numRegs);
+    }
+    const int occ_regs = 65536 / (((regs + 7) / 8 * 8) * kPairThreads);
+    const int occ = std::max(1, std::min(occ_regs, g.occ));
+    const int grid = std::min(a.n_tiles, h->sm_count * occ);
     const double C = a.N;
     const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
     const double bytes = (double)B * T * C * ESZ * (out ? 2 : 1) +
                          (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     h->prof_begin(st, label, flops, bytes);
-    tc_pair_kernel<BF16><<<grid, kPairThreads, g.smem, st>>>(a);
+    if (two) tc_pair_kernel<BF16, 2><<<grid, kPairThreads, g.smem, st>>>(a);
+    else tc_pair_kernel<BF16, 1><<<grid, kPairThreads, g.smem, st>>>(a);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
 }
@@ -321,7 +357,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         a.N = tc_pick_n(L.cout);
         a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
         const int n_kb = (in.nchunks + 7) / 8;
-        a.w_ntile_stride = (long long)n_kb * L.k * 8 * a.N * 16;
+        a.w_ntile_stride = (long long)in.nchunks * L.k * a.N * 16;
         a.w_phase_stride = 0;
         a.bias = L.bias;
         const TcPlane& og = out ? *out : *res;               // geometry of out/res planes
@@ -355,7 +391,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             a.N = tc_pick_n(U.cout);
             a.w = reinterpret_cast<const uint8_t*>(BF16 ? U.tc.w_bf16 : U.tc.w_tf32);
             const int n_kb = (cur->nchunks + 7) / 8;
-            a.w_ntile_stride = (long long)n_kb * U.taps_max * 8 * a.N * 16;
+            a.w_ntile_stride = (long long)cur->nchunks * U.taps_max * a.N * 16;
             a.w_phase_stride = a.w_ntile_stride * (U.cout / a.N);
             a.bias = U.bias;
             a.out = ptr(S.X); a.res = nullptr; a.o_bstride = S.X.bstride; a.o_pstride = S.X.pstride;
@@ -436,7 +472,7 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     a.a = (uint8_t*)ws + in.off; a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
     a.N = tc_pick_n(L.cout);
     a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
-    a.w_ntile_stride = (long long)((in.nchunks + 7) / 8) * L.k * 8 * a.N * 16;
+    a.w_ntile_stride = (long long)in.nchunks * L.k * a.N * 16;
     a.bias = L.bias;
     a.out = (uint8_t*)ws + out.off; a.res = which ? (uint8_t*)ws + res.off : nullptr;
     a.o_bstride = out.bstride; a.o_pstride = out.pstride;
@@ -486,8 +522,10 @@ inline void configure_kernels(hfg_handle*) {
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
 }
 
 }  // namespace hfg
