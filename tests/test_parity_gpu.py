@@ -224,3 +224,20 @@ def test_long_form_against_oracle():
         err = float(np.abs(wav - ref).max())
         print(f"long-form[{mode}] max-abs {err:.3e}")
         assert err <= TOL[mode]
+
+
+def test_geometry_outside_umma_shapes_falls_back_to_fp32_kernels():
+    """Channel counts that are not multiples of 16 (40 -> 20 -> 10) cannot use the UMMA tiles; the
+    module must stay on the GPU (fp32 kernels), warn, and still match the oracle."""
+    import oracle
+    cfg = dict(n_mels=12, upsample_rates=[3, 2], upsample_kernel_sizes=[7, 4], upsample_initial_channel=40,
+               resblock_kernel_sizes=[3, 5], resblock_dilation_sizes=[[1, 2], [2, 6]])
+    sd = synth.make_weights(cfg, 77)
+    mel = synth.make_mel(78, 2, 12, 41)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    gen = make_gen(cfg, sd, "tf32")
+    with pytest.warns(UserWarning, match="fp32 CUDA kernels"):
+        wav = run(gen, mel)
+    assert gen.mode == "fp32" and gen.last_launch_count > 0
+    assert wav.shape == ref.shape
+    assert float(np.abs(wav - ref).max()) <= 2e-5

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import math
 import os
+import warnings
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -244,14 +245,27 @@ class HiFiGANGenerator(nn.Module):
             for i in range(self.num_upsamples):
                 print(f"[HiFiGANGenerator] After upsample {i}: {torch.Size(shapes[i + 1])}")
                 print(f"[HiFiGANGenerator] After MRF {i}: {torch.Size(shapes[i + 1])}")
-        mode = _capi.MODES[self.mode]
-        if mel.is_cuda:
-            wav = self._forward_cuda(mel.contiguous(), shapes, mode, _stages)
-        else:
-            wav = self._forward_host(mel.contiguous(), shapes, mode)
+        try:
+            wav = self._dispatch(mel, shapes, _capi.MODES[self.mode], _stages)
+        except _capi.HfgError as e:
+            # geometry the UMMA shapes do not cover (channel counts not multiples of 16): the fp32
+            # CUDA kernels handle any geometry.  Still the GPU -- there is no CPU path.
+            if e.code != _capi.ERR_UNSUPPORTED or self.mode == "fp32":
+                raise
+            warnings.warn(f"HiFiGANGenerator: mode {self.mode!r} unsupported for this geometry "
+                          f"({e}); using the fp32 CUDA kernels")
+            self.mode = "fp32"
+            if _stages is not None:
+                _stages.clear()
+            wav = self._dispatch(mel, shapes, _capi.MODES["fp32"], _stages)
         if self.debug_shapes:
             print(f"[HiFiGANGenerator] Output wav shape: {wav.shape}")
         return wav
+
+    def _dispatch(self, mel, shapes, mode, stages):
+        if mel.is_cuda:
+            return self._forward_cuda(mel.contiguous(), shapes, mode, stages)
+        return self._forward_host(mel.contiguous(), shapes, mode)
 
     def _forward_cuda(self, mel, shapes, mode, stages):
         dev = mel.device
