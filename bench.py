@@ -237,6 +237,47 @@ def main():
         e2e_s = time.perf_counter() - t0
         barrier()
 
+        # ---------------- other arithmetic modes + output quality (untimed for `value`) ----------------
+        # the same batch in the strict fp32 mode is the on-device stand-in for the reference output
+        # (fp32 mode matches the reference to 3e-8: tests/test_parity_gpu.py, profiles/)
+        quality, other = {}, {}
+        if rank == 0:
+            from tts_sambert_hifigan_b200 import metrics
+            sd = gen.state_dict()
+            outs = {args.mode: wav}
+            for m in ("fp32", "tf32", "bf16"):
+                if m == args.mode:
+                    continue
+                g2 = pkg.HiFiGANGenerator(**cfg, mode=m).to(dev)
+                g2.load_state_dict(sd)
+                for _ in range(3):
+                    outs[m] = g2(mel)
+                if m != "fp32":
+                    n2 = max(3, steps // 2)
+                    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n2)]
+                    for s2 in range(n2):
+                        flush.fill_(s2 & 0xFF)
+                        ev2[s2][0].record()
+                        outs[m] = g2(mel)
+                        ev2[s2][1].record()
+                    torch.cuda.synchronize()
+                    ms2 = sum(a.elapsed_time(b) for a, b in ev2) / n2
+                    other[m] = {"ms_per_step": ms2, "value_per_gpu": audio_seconds(B, T) / (ms2 / 1e3),
+                                "tflops_per_gpu": synth.flops_per_frame(cfg) * B * T / (ms2 / 1e3) / 1e12}
+                del g2
+            torch.cuda.synchronize()
+            ref32 = outs["fp32"]
+            for m in ("tf32", "bf16"):
+                q = {"max_abs_vs_fp32_mode": float((outs[m] - ref32).abs().max()),
+                     "ref_peak": float(ref32.abs().max())}
+                try:
+                    q["log_mel_l1_vs_fp32_mode"] = metrics.log_mel_l1(ref32, outs[m])
+                except Exception as e:  # torchaudio missing on the box
+                    q["log_mel_l1_vs_fp32_mode"] = None
+                    q["log_mel_note"] = f"unavailable: {type(e).__name__}"
+                quality[m] = q
+        barrier()
+
         # ---------------- per-kernel profile (separate, untimed pass) ----------------
         h = gen._handle_for(dev)
         h.set_profiling(True)
@@ -301,6 +342,8 @@ def main():
                     "d2h_bytes_per_step": int(wav_host.numel() * 4),
                     "steps": e2e_steps},
             "gpu_launches": int(launches_per_step * steps),
+            "quality": quality,
+            "other_modes": other,
             "clocks": clocks,
             "roofline": roofline,
         }

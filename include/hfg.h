@@ -119,6 +119,13 @@ int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32
 int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
                      float* wav_host, int32_t mode);
 
+/* Same with hints: a buffer flagged as page-locked (cudaHostAlloc / torch pin_memory) is used
+ * for the DMA directly instead of being staged through the handle's own pinned buffer. */
+#define HFG_HOST_MEL_PINNED 1u
+#define HFG_HOST_WAV_PINNED 2u
+int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
+                        float* wav_host, int32_t mode, uint32_t flags);
+
 /* Per-launch device timing.  When enabled, every kernel launch of hfg_forward*
  * is bracketed by a CUDA event pair on the launching stream; hfg_get_profile
  * synchronises and returns a JSON array, one entry per kernel label:

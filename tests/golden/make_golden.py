@@ -137,3 +137,9 @@ if __name__ == "__main__":
     manifest["debug_print_lines"] = wrapper_case()
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1)
+
+
+# The log-mel-L1 metric pin (manifest["logmel_l1_pin"]) is produced by running the reference's
+# VocoderLoss(mel_config=metrics.AUDIO, loss_mode="mel_only").mel_reconstruction_loss(a, b)
+# (reference models/losses.py:708-797) on a = 0.05*normal(101), b = a + 0.002*normal(102),
+# shape [2,1,8192]; see tests/test_oracle.py::test_logmel_metric_matches_reference.

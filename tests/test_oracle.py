@@ -74,3 +74,14 @@ def test_output_length_formula():
 def test_flop_model():
     # 614.105 MFLOP per mel frame for the default config
     assert abs(synth.flops_per_frame(synth.DEFAULT_CONFIG) / 1e6 - 614.105) < 0.01
+
+
+def test_logmel_metric_matches_reference(manifest):
+    """metrics.log_mel_l1 restates reference models/losses.py:708-797; pinned to the value the
+    reference's own VocoderLoss.mel_reconstruction_loss returned here."""
+    pytest.importorskip("torchaudio")
+    from tts_sambert_hifigan_b200 import metrics
+    p = manifest["logmel_l1_pin"]
+    a = torch.from_numpy(synth.normal(p["seed_a"], p["shape"])) * p["scale_a"]
+    b = a + torch.from_numpy(synth.normal(p["seed_b"], p["shape"])) * p["scale_b"]
+    assert abs(metrics.log_mel_l1(a, b) - p["value"]) <= 1e-5 * max(1.0, abs(p["value"]))

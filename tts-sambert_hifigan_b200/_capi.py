@@ -15,7 +15,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2
 SYMBOLS = [
     "hfg_abi_version", "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_weight",
     "hfg_commit_weights", "hfg_out_len", "hfg_workspace_bytes", "hfg_forward",
-    "hfg_forward_stages", "hfg_forward_host", "hfg_last_launch_count",
+    "hfg_forward_stages", "hfg_forward_host", "hfg_forward_host_ex", "hfg_last_launch_count",
     "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer",
 ]
 
@@ -85,6 +85,8 @@ def load():
                                        ctypes.POINTER(vp)]
     lib.hfg_forward_host.restype = ctypes.c_int
     lib.hfg_forward_host.argtypes = [vp, vp, i32, i32, vp, i32]
+    lib.hfg_forward_host_ex.restype = ctypes.c_int
+    lib.hfg_forward_host_ex.argtypes = [vp, vp, i32, i32, vp, i32, ctypes.c_uint32]
     lib.hfg_last_launch_count.restype = ctypes.c_int
     lib.hfg_last_launch_count.argtypes = [vp, i64p]
     lib.hfg_set_profiling.restype = ctypes.c_int
@@ -179,8 +181,10 @@ class Handle:
                                               mode, ctypes.c_void_p(stream), arr)
         self._check(rc)
 
-    def forward_host(self, mel_ptr: int, batch: int, frames: int, wav_ptr: int, mode: int):
-        self._check(self._lib.hfg_forward_host(self._h, mel_ptr, batch, frames, wav_ptr, mode))
+    def forward_host(self, mel_ptr: int, batch: int, frames: int, wav_ptr: int, mode: int,
+                     mel_pinned: bool = False, wav_pinned: bool = False):
+        flags = (1 if mel_pinned else 0) | (2 if wav_pinned else 0)
+        self._check(self._lib.hfg_forward_host_ex(self._h, mel_ptr, batch, frames, wav_ptr, mode, flags))
 
     def set_profiling(self, on: bool):
         self._check(self._lib.hfg_set_profiling(self._h, 1 if on else 0))

@@ -494,6 +494,11 @@ int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32
 
 int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
                      float* wav_host, int32_t mode) {
+    return hfg_forward_host_ex(h, mel_host, batch, frames, wav_host, mode, 0);
+}
+
+int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
+                        float* wav_host, int32_t mode, uint32_t flags) {
     if (!h) return HFG_ERR_INVALID;
     HFG_TRY(h)
     if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
@@ -508,13 +513,16 @@ int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_
     if (mode == HFG_MODE_FP32) ws_bytes = workspace_fp32(h, batch, frames);
     else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) ws_bytes = tc_workspace_bytes(h, batch, frames, mode);
     else throw StatusError(HFG_ERR_INVALID, "unknown mode");
-    h->ensure_host_path(mel_bytes, wav_bytes, ws_bytes);
-    memcpy(h->pin_mel, mel_host, mel_bytes);
-    check_cuda(cudaMemcpyAsync(h->dev_mel, h->pin_mel, mel_bytes, cudaMemcpyHostToDevice, h->stream), "H2D mel");
+    const bool mel_pinned = (flags & HFG_HOST_MEL_PINNED) != 0, wav_pinned = (flags & HFG_HOST_WAV_PINNED) != 0;
+    h->ensure_host_path(mel_pinned ? 0 : mel_bytes, wav_pinned ? 0 : wav_bytes, mel_bytes, wav_bytes, ws_bytes);
+    const float* src = mel_host;
+    if (!mel_pinned) { memcpy(h->pin_mel, mel_host, mel_bytes); src = h->pin_mel; }
+    check_cuda(cudaMemcpyAsync(h->dev_mel, src, mel_bytes, cudaMemcpyHostToDevice, h->stream), "H2D mel");
     do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
-    check_cuda(cudaMemcpyAsync(h->pin_wav, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
+    float* dst = wav_pinned ? wav_host : h->pin_wav;
+    check_cuda(cudaMemcpyAsync(dst, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
     check_cuda(cudaStreamSynchronize(h->stream), "stream sync");
-    memcpy(wav_host, h->pin_wav, wav_bytes);
+    if (!wav_pinned) memcpy(wav_host, h->pin_wav, wav_bytes);
     HFG_CATCH(h)
 }
 

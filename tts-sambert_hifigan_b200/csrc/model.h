@@ -135,7 +135,8 @@ struct hfg_handle {
         device_allocs.clear();
         committed = false;
     }
-    void ensure_host_path(size_t mel_bytes, size_t wav_bytes, size_t ws_bytes) {
+    void ensure_host_path(size_t pin_mel_need, size_t pin_wav_need, size_t mel_bytes, size_t wav_bytes,
+                          size_t ws_bytes) {
         using hfg::check_cuda;
         if (!stream) check_cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
         auto grow_pin = [](float*& p, size_t& have, size_t want) {
@@ -152,8 +153,8 @@ struct hfg_handle {
             check_cuda(cudaMalloc(p, want), "cudaMalloc");
             have = want;
         };
-        grow_pin(pin_mel, pin_mel_bytes, mel_bytes);
-        grow_pin(pin_wav, pin_wav_bytes, wav_bytes);
+        if (pin_mel_need) grow_pin(pin_mel, pin_mel_bytes, pin_mel_need);
+        if (pin_wav_need) grow_pin(pin_wav, pin_wav_bytes, pin_wav_need);
         grow_dev((void**)&dev_mel, dev_mel_bytes, mel_bytes);
         grow_dev((void**)&dev_wav, dev_wav_bytes, wav_bytes);
         grow_dev(&dev_ws, dev_ws_bytes, ws_bytes);

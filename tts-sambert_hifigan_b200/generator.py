@@ -293,7 +293,9 @@ class HiFiGANGenerator(nn.Module):
         dev = torch.device("cuda", torch.cuda.current_device())
         B, _, T = mel.shape
         h = self._handle_for(dev)
-        wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32)
-        h.forward_host(mel.data_ptr(), B, T, wav.data_ptr(), mode)
+        # the result is written by DMA straight into a page-locked tensor (torch caches these)
+        wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32, pin_memory=True)
+        h.forward_host(mel.data_ptr(), B, T, wav.data_ptr(), mode,
+                       mel_pinned=mel.is_pinned(), wav_pinned=True)
         self.last_launch_count = h.last_launch_count()
         return wav
