@@ -36,6 +36,9 @@ struct HostTensor {
 struct TcPack {
     void* w_bf16 = nullptr;   // bf16 operand tiles
     void* w_tf32 = nullptr;   // fp32 (consumed as tf32) operand tiles
+    // the same weights split into two N-halves, one per CTA of a cta_group::2 pair
+    void* w_bf16_h2 = nullptr; long long h2_stride_bf16 = 0;
+    void* w_tf32_h2 = nullptr; long long h2_stride_tf32 = 0;
     bool ok = false;          // layer shape is covered by the tensor-core path
 };
 

@@ -118,6 +118,50 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// CTA-pair commit: arrives on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.  RELAXED on purpose: these
+// barriers only carry the event "my stage has landed / my H tile is written" to the leader, which then
+// ISSUES the pair MMA; the data itself is read by the tensor core of the SM that owns it (its own smem /
+// TMEM), never by the leader's threads, so no cross-CTA memory ordering is needed.  The default
+// release.cluster / acquire.cluster forms compile to MEMBAR.ALL.GPU and CCTL.IVALL per stage and made the
+// CTA-pair kernel 1.5x slower than the single-CTA one (profiles/r1_tuning.md).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 r;\n\tmapa.shared::cluster.u32 r, %0, %1;\n\t"
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [r];\n\t}"
+        ::"r"(bar), "r"(cta) : "memory");
+}
+// wait for an arrival that came from the peer CTA (relaxed, see above)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok, spins = 0;
+    long long t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && (++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    } while (!ok);
+}
 // UMMA shared-memory descriptor, K-major, SWIZZLE_NONE ("interleaved" core matrices):
 //   bits [0,14) start>>4, [16,30) LBO>>4 (stride between K-adjacent core matrices),
 //   [32,46) SBO>>4 (stride between 8-row groups), [46,48) version = 1, [61,64) layout = 0
@@ -127,9 +171,25 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
 }
 // UMMA instruction descriptor: fp32 accumulate, K-major A and B, M = 128
 template <bool BF16>
-__device__ __forceinline__ uint32_t umma_idesc(int N) {
+__device__ __forceinline__ uint32_t umma_idesc(int N, int M = 128) {
     const uint32_t fmt = BF16 ? 1u : 2u;            // 1 = BF16, 2 = TF32
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// cta_group::2: one instruction drives the tensor cores of both SMs of a CTA pair (M = 256: each CTA
+// supplies its own 128 rows of A and HALF of the N rows of B from the same smem offsets)
+template <bool BF16>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
 }
 template <bool BF16>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -148,18 +208,23 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
 // One (tap, sub-tile): `ksteps` K-steps of UMMA_K (two 16-byte cells each), A and B descriptors
 // advanced by 2 cells per step.  The common 4-step case is straight-line code so the
 // UTCHMMAs issue back to back from uniform registers.
-template <bool BF16>
+template <bool BF16, int CTAS = 1>
+__device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    if constexpr (CTAS == 2) umma2<BF16>(d, ad, bd, idesc, acc);
+    else umma<BF16>(d, ad, bd, idesc, acc);
+}
+template <bool BF16, int CTAS = 1>
 __device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t a_step, uint32_t b_step, uint32_t idesc, int ksteps,
                                             uint32_t acc_first) {
     if (ksteps == 4) {
-        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first);
-        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + a_step), ((uint64_t)hi << 32) | (b_lo + b_step), idesc, 1u);
-        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 2 * a_step), ((uint64_t)hi << 32) | (b_lo + 2 * b_step), idesc, 1u);
-        umma<BF16>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 3 * a_step), ((uint64_t)hi << 32) | (b_lo + 3 * b_step), idesc, 1u);
+        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first);
+        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + a_step), ((uint64_t)hi << 32) | (b_lo + b_step), idesc, 1u);
+        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 2 * a_step), ((uint64_t)hi << 32) | (b_lo + 2 * b_step), idesc, 1u);
+        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 3 * a_step), ((uint64_t)hi << 32) | (b_lo + 3 * b_step), idesc, 1u);
     } else {
         for (int s = 0; s < ksteps; ++s) {
-            umma<BF16>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first | (uint32_t)s);
+            umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first | (uint32_t)s);
             a_lo += a_step;
             b_lo += b_step;
         }

@@ -35,7 +35,8 @@ constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
 
 struct TcPairArgs {
     const uint8_t* a; long long a_bstride, a_pstride;     // leaky_relu(x) planes
-    const uint8_t* w1; const uint8_t* w2;                 // packed [kb][tap][8][N][16 B]
+    const uint8_t* w1; const uint8_t* w2;                 // packed [kb][tap][chunk][N][16 B]; CTA pair: [half][..][N/2][16 B]
+    long long w_half_stride;                              // bytes between the two N-halves (CTA pair only)
     const float* b1; const float* b2;
     uint8_t* out; long long o_bstride, o_pstride;         // leaky_relu(x_new) planes (may be null)
     float* acc; long long acc_bstride, acc_pstride;       // MRF fp32 partial sums (bytes)
@@ -68,7 +69,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // MINB = CTAs per SM the register allocation must allow (2 for the narrow layers, whose tiles are
 // latency-bound and want a second CTA to fill the tensor pipe while the first one is in an epilogue)
-template <bool BF16, int MINB>
+// CTAS = 2: a cluster of two CTAs runs two adjacent tiles in lockstep; the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) for both, each CTA stages only its half of every weight tile
+// (half the L2->smem weight traffic and half the B-operand smem reads per SM).
+template <bool BF16, int MINB, int CTAS>
 __global__ void __launch_bounds__(kPairThreads, MINB)
 tc_pair_kernel(const TcPairArgs a) {
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
@@ -77,12 +81,14 @@ tc_pair_kernel(const TcPairArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, MT = a.MT, R1 = a.R1, RH = a.RH, k = a.k;
+    const int NB = N / CTAS;                          // rows of the weight tile staged by this CTA
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const int n_chunks = a.n_chunks;
     const int nck_max = n_chunks < 8 ? n_chunks : 8;
     const int n_kb = (n_chunks + 7) / 8;
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
     const int G = a.tap_group;
-    const uint32_t w_stage_bytes = (uint32_t)G * N * nck_max * 16;
+    const uint32_t w_stage_bytes = (uint32_t)G * NB * nck_max * 16;
     uint8_t* sA = smem;
     uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
     uint8_t* sH = sW + (size_t)a.sw * w_stage_bytes;
@@ -96,7 +102,9 @@ tc_pair_kernel(const TcPairArgs a) {
     auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxSA + kMaxSW + i); };
     const uint32_t ACC1_FULL = bar0 + 8u * (2 * kMaxSA + 2 * kMaxSW);
     const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 3);
+    auto PEER_A_FULL = [&](int i) { return ACC1_FULL + 24 + 8u * i; };            // leader only: peer's stages landed
+    auto PEER_W_FULL = [&](int i) { return ACC1_FULL + 24 + 8u * (kMaxSA + i); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 3 + kMaxSA + kMaxSW);
 
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * N) ncols <<= 1;
@@ -105,23 +113,41 @@ tc_pair_kernel(const TcPairArgs a) {
         for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), 1); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
         for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), 1); mbar_init(W_EMPTY(i), 1); }
         mbar_init(ACC1_FULL, 1);
-        mbar_init(H_READY, kPairEpiWarps);
+        mbar_init(H_READY, kPairEpiWarps * CTAS);
         mbar_init(ACC2_FULL, 1);
+        if constexpr (CTAS == 2) {
+            for (int i = 0; i < a.sa; ++i) mbar_init(PEER_A_FULL(i), 1);
+            for (int i = 0; i < a.sw; ++i) mbar_init(PEER_W_FULL(i), 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32(tmem_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < N; i += 32 * kPairEpiWarps) { sB1[i] = a.b1[i]; sB2[i] = a.b2[i]; }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();      // peer barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc1 = tmem_base, acc2 = tmem_base + (uint32_t)(MT * N);
+    // tile schedule: cluster c takes tile pairs c, c + n_clusters, ...; CTA `rank` runs tile 2*pair + rank.
+    // An odd tail tile is duplicated on the peer (same coordinates, stores suppressed) so both CTAs
+    // stay in lockstep on the shared weight ring.
+    const int n_sched = (a.n_tiles + CTAS - 1) / CTAS;
+    const int sched0 = (int)blockIdx.x / CTAS, sched_step = (int)gridDim.x / CTAS;
+    auto tile_of = [&](int sc) { const int t = sc * CTAS + (int)rank; return t < a.n_tiles ? t : a.n_tiles - 1; };
+    auto tile_real = [&](int sc) { return sc * CTAS + (int)rank < a.n_tiles; };
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -150,18 +176,19 @@ tc_pair_kernel(const TcPairArgs a) {
             const int g = (k - tap0) < G ? (k - tap0) : G;
             mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
             if (leader) {
-                mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * N * 16);
+                mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
                 bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
-                         w + ((long long)kb * k * 8 + (long long)tap0 * nck) * N * 16, (uint32_t)g * nck * N * 16,
-                         W_FULL(sw_i));
+                         w + (long long)rank * a.w_half_stride +
+                             ((long long)kb * k * 8 + (long long)tap0 * nck) * NB * 16,
+                         (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
             }
             __syncwarp();
             if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
         };
-        if ((int)blockIdx.x < a.n_tiles) issue_a(tile_src(blockIdx.x), 0);
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            const uint8_t* ab = tile_src(tile);
-            const int next = tile + (int)gridDim.x;
+        if (sched0 < n_sched) issue_a(tile_src(tile_of(sched0)), 0);
+        for (int sc = sched0; sc < n_sched; sc += sched_step) {
+            const uint8_t* ab = tile_src(tile_of(sc));
+            const int next = sc + sched_step;
             for (int kb = 0; kb < n_kb; ++kb)
                 for (int tap = 0; tap < k; tap += G) {
                     issue_w(a.w1, kb, tap);
@@ -171,55 +198,80 @@ tc_pair_kernel(const TcPairArgs a) {
                 for (int tap = 0; tap < k; tap += G) {
                     issue_w(a.w2, kb, tap);
                     // first K block of the NEXT tile: lands while conv2 of this tile still runs
-                    if (kb == 0 && tap == 0 && next < a.n_tiles) issue_a(tile_src(next), 0);
+                    if (kb == 0 && tap == 0 && next < n_sched) issue_a(tile_src(tile_of(next)), 0);
                 }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<BF16>(N);
+        const uint32_t idesc = umma_idesc<BF16>(N, 128 * CTAS);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
-        const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)N) << 16;
+        const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)NB) << 16;
+        auto commit = [&](uint32_t bar) { if constexpr (CTAS == 2) tc_commit2(bar); else tc_commit(bar); };
+        if (CTAS == 2 && rank == 1) {
+            // ---- peer CTA: no MMA issue.  Forward "my stage has landed" to the leader: one lane per ring
+            // slot, so slots are forwarded independently instead of through one serial wait chain ----
+            const int n_my = sched0 < n_sched ? (n_sched - sched0 + sched_step - 1) / sched_step : 0;
+            const int stages_per_tile = 2 * n_kb * ((k + G - 1) / G);
+            const int total_w = n_my * stages_per_tile, total_a = n_my * n_kb;
+            if (lane < a.sw) {
+                const int uses = total_w / a.sw + (lane < total_w % a.sw ? 1 : 0);
+                for (int u = 0; u < uses; ++u) {
+                    mbar_wait(W_FULL(lane), (uint32_t)(u & 1));
+                    mbar_arrive_remote(PEER_W_FULL(lane), 0);
+                }
+            } else if (lane < a.sw + a.sa) {
+                const int sl = lane - a.sw;
+                const int uses = total_a / a.sa + (sl < total_a % a.sa ? 1 : 0);
+                for (int u = 0; u < uses; ++u) {
+                    mbar_wait(A_FULL(sl), (uint32_t)(u & 1));
+                    mbar_arrive_remote(PEER_A_FULL(sl), 0);
+                }
+            }
+            __syncwarp();
+        } else {
         const uint32_t h_lo_base = ((smem_u32(sH) & 0x3FFFFu) >> 4) | h_lbo;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        for (int sc = sched0; sc < n_sched; sc += sched_step, ++it) {
             // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1 ----
             uint32_t acc_on = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
                 const int ksteps = nck >> 1;
                 mbar_wait(A_FULL(sa_i), sa_ph);
+                if constexpr (CTAS == 2) mbar_wait_cluster(PEER_A_FULL(sa_i), sa_ph);
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
+                    if constexpr (CTAS == 2) mbar_wait_cluster(PEER_W_FULL(sw_i), sw_ph);
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
                         for (int tt = 0; tt < g; ++tt) {
-                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
+                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
                             const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil);
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<BF16>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                  2u * (uint32_t)R1, 2u * (uint32_t)N, idesc, ksteps,
-                                                  acc_on | (uint32_t)tt);
+                                umma_ksteps<BF16, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                        2u * (uint32_t)R1, 2u * (uint32_t)NB, idesc, ksteps,
+                                                        acc_on | (uint32_t)tt);
                         }
-                        tc_commit(W_EMPTY(sw_i));
+                        commit(W_EMPTY(sw_i));
                     }
                     __syncwarp();
                     acc_on = 1;
                     if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                 }
-                if (leader) tc_commit(A_EMPTY(sa_i));
+                if (leader) commit(A_EMPTY(sa_i));
                 __syncwarp();
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
             }
-            if (leader) tc_commit(ACC1_FULL);
+            if (leader) commit(ACC1_FULL);
             __syncwarp();
             // ---- conv2: acc2 (pre-loaded with x + b2) += sum_{kb,tap} H(+tap rows) * W2 ----
-            mbar_wait(H_READY, it & 1);
+            if constexpr (CTAS == 2) mbar_wait_cluster(H_READY, it & 1); else mbar_wait(H_READY, it & 1);
             tc_fence_after();
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
@@ -228,25 +280,27 @@ tc_pair_kernel(const TcPairArgs a) {
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
+                    if constexpr (CTAS == 2) mbar_wait_cluster(PEER_W_FULL(sw_i), sw_ph);
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
                         for (int tt = 0; tt < g; ++tt) {
-                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
+                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
                             const uint32_t h_lo1 = h_lo0 + (uint32_t)(tap0 + tt);
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<BF16>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                  2u * (uint32_t)RH, 2u * (uint32_t)N, idesc, ksteps, 1u);
+                                umma_ksteps<BF16, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc, ksteps, 1u);
                         }
-                        tc_commit(W_EMPTY(sw_i));
+                        commit(W_EMPTY(sw_i));
                     }
                     __syncwarp();
                     if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                 }
             }
-            if (leader) tc_commit(ACC2_FULL);
+            if (leader) commit(ACC2_FULL);
             __syncwarp();
         }
+        }   // leader / single-CTA issue path
     } else {
         // ===================== epilogue warps =====================
         const int e = warp - 2;
@@ -260,7 +314,9 @@ tc_pair_kernel(const TcPairArgs a) {
         const bool acc_store_mode = (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD);
         int sa_i = 0, sa_ph = 0;
         uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        for (int sc = sched0; sc < n_sched; sc += sched_step, ++it) {
+            const int tile = tile_of(sc);
+            const bool real = tile_real(sc);          // false: duplicated tail tile, no global side effects
             const int b = tile / a.tiles_per_batch;
             const int t0 = (tile % a.tiles_per_batch) * a.TO;
             // ---------- pre2: acc2 <- x + b2 (+ partial MRF sum), per K block as it lands ----------
@@ -271,7 +327,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 for (int mt = half; mt < MT; mt += 2) {
                     const int lr = mt * 128 + row;                      // output row inside the tile
                     const int t = t0 + lr;
-                    const bool add_prev = add_prev_mode && lr < a.TO && t < a.T;
+                    const bool add_prev = add_prev_mode && real && lr < a.TO && t < a.T;
                     const uint8_t* rp = sa_p + (size_t)(lr + a.p2 + a.p1) * 16;
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
@@ -332,14 +388,17 @@ tc_pair_kernel(const TcPairArgs a) {
             fence_async_smem();          // H (generic-proxy writes) must be visible to the MMA (async proxy)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(H_READY);
+            if (lane == 0) {
+                if (CTAS == 2 && rank == 1) mbar_arrive_remote(H_READY, 0);
+                else mbar_arrive(H_READY);
+            }
             // ---------- epi2: acc2 -> global ----------
             mbar_wait(ACC2_FULL, it & 1);
             tc_fence_after();
             for (int mt = half; mt < MT; mt += 2) {
                 const int lr = mt * 128 + row;
                 const int t = t0 + lr;
-                const bool valid = lr < a.TO && t < a.T;
+                const bool valid = real && lr < a.TO && t < a.T;
                 const long long row_bytes = (long long)(kPadL + t) * 16;
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N);
                 uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
@@ -377,9 +436,13 @@ tc_pair_kernel(const TcPairArgs a) {
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CTAS == 2) cluster_sync_all();      // nobody exits while the peer may still signal / read it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+        if constexpr (CTAS == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
 

@@ -47,10 +47,14 @@ static inline bool tc_shape_ok(int cin, int cout) { return cin % 16 == 0 && cout
 // channel ci at tap `tap` of phase `phase` for output channel n (0 outside the kernel).
 // Layout: [phase][ntile][kb][tap][chunk(8)][n(N)][cell(CW)], cells of 16 bytes.
 template <typename F>
-static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int phases, int taps_max, F get) {
-    tp.ok = tc_shape_ok(cin, cout);
-    if (!tp.ok) return;
-    const int N = tc_pick_n(cout), ntiles = cout / N;
+static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int phases, int taps_max, F get,
+                            bool halves = false) {
+    if (!halves) {
+        tp.ok = tc_shape_ok(cin, cout);
+        if (!tp.ok) return;
+    }
+    // halves: two N/2-wide tiles (one per CTA of a pair) in the same [ntile][kb][tap][chunk][n] layout
+    const int N = halves ? cout / 2 : tc_pick_n(cout), ntiles = cout / N;
     for (int bf = 0; bf < 2; ++bf) {
         const int CW = bf ? 8 : 4;
         const int nchunks = cin / CW, nkb = (nchunks + 7) / 8;
@@ -83,15 +87,24 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
                     }
                 }
         void* d = h->upload(buf);
-        if (bf) tp.w_bf16 = d; else tp.w_tf32 = d;
+        if (halves) {
+            if (bf) { tp.w_bf16_h2 = d; tp.h2_stride_bf16 = (long long)per_tile; }
+            else { tp.w_tf32_h2 = d; tp.h2_stride_tf32 = (long long)per_tile; }
+        } else {
+            if (bf) tp.w_bf16 = d; else tp.w_tf32 = d;
+        }
     }
 }
 
 inline void tc_pack_conv(hfg_handle* h, ConvLayer& L, const HostTensor& w, const HostTensor&) {
     const int cin = L.cin, k = L.k;
-    tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, [&](int n, int ci, int, int tap) {
+    auto get = [&](int n, int ci, int, int tap) {
         return w.data[((size_t)n * cin + ci) * k + tap];                // Conv1d weight [C_out, C_in, k]
-    });
+    };
+    tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get);
+    // CTA-pair layout for the fused ResBlock kernel (square convs, N <= 256, N/2 a UMMA-legal half)
+    if (L.tc.ok && L.cin == L.cout && L.cout <= 256 && L.cout % 32 == 0)
+        tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, /*halves=*/true);
 }
 inline void tc_pack_up(hfg_handle* h, UpLayer& L, const HostTensor& w, const HostTensor&) {
     const int cout = L.cout, k = L.k, u = L.u;
@@ -224,9 +237,19 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
 }
 
 // ---- fused ResBlock pair ----
-struct PairGeom { int MT, sa, sw, G, R1, RH, TO; size_t smem; int occ; bool ok; };
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas; size_t smem; int occ; bool ok; };
 
-static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks) {
+static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
+    // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
+    // (profiles/r1_tuning.md): C = 64..128 with k >= 5 in bf16, C = 64..128 for every k in tf32.  C = 256
+    // (TMEM-limited to one 128-row sub-tile per CTA) and C = 32 stay single-CTA.
+    const int N = P.c1.cout;
+    const int dflt = (N >= 64 && N <= 128 && (P.c1.k >= 5 || !bf16)) ? 2 : 1;
+    const int want = env_int("HFG_TC_PAIR_CTAS", dflt);
+    return (want == 2 && P.c1.tc.w_bf16_h2 && P.c2.tc.w_bf16_h2) ? 2 : 1;
+}
+
+static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, bool bf16) {
     PairGeom g{};
     const int N = P.c1.cout, k = P.c1.k, p1 = P.c1.pad, p2 = P.c2.pad;
     g.ok = false;
@@ -235,6 +258,8 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
     const int nck_max = std::min(8, n_chunks), n_kb = (n_chunks + 7) / 8;
     const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
+    const int ctas = tc_pair_ctas(P, bf16);
+    const int NB = N / ctas;                                              // weight rows staged per CTA
     // Candidates from the largest tile down.  Measured rule (profiles/r1_tuning.md): two co-resident
     // CTAs per SM beat one CTA with a larger tile (one CTA's epilogue hides behind the other's MMAs),
     // so take the largest MT that still allows 2 CTAs/SM, else the largest MT that fits.
@@ -242,24 +267,38 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     best.ok = false;
     for (int MT : {4, 2, 1}) {
         if (MT > mt_cap || 2 * MT * N > 512) continue;
-        for (int sw : {4, 3, 2}) {
-            const int G = tc_tap_group(N, nck_max, k);
-            if (G > 1 && sw > 2) continue;                                // fat stages: two are enough
-            const int sa = std::min(kMaxSA, n_kb);
-            const int R1 = MT * 128 + 2 * p1;
-            const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
-            const size_t smem = (size_t)sa * R1 * nck_max * 16 + (size_t)sw * G * N * nck_max * 16 +
-                                (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 256;
-            if (smem > (size_t)kTcSmemLimit) continue;
+        // W ring: as deep as shared memory allows (<= 8 stages).  The refill loop of a stage is
+        // "MMA done -> commit -> producer -> L2 -> smem (-> peer forward)", about 1-2 us, so the ring must
+        // hold that much MMA work; when a second CTA can share the SM, stop at the depth that keeps it.
+        const int G = tc_tap_group(NB, nck_max, k);
+        const int sa = std::min(kMaxSA, n_kb);
+        const int R1 = MT * 128 + 2 * p1;
+        const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
+        const size_t stage = (size_t)G * NB * nck_max * 16;
+        const size_t fixed = (size_t)sa * R1 * nck_max * 16 + (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 384;
+        int ncols = 32;
+        while (ncols < 2 * MT * N) ncols <<= 1;
+        auto make = [&](int sw) {
             PairGeom c{};
-            c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2; c.smem = smem;
-            int ncols = 32;
-            while (ncols < 2 * MT * N) ncols <<= 1;
-            c.occ = std::max(1, std::min((int)((227 * 1024) / (smem + 1024)), 512 / ncols));
+            c.ctas = ctas;
+            c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2;
+            c.smem = fixed + (size_t)sw * stage;
+            c.occ = std::max(1, std::min((int)((227 * 1024) / (c.smem + 1024)), 512 / ncols));
             c.ok = true;
-            if (!best.ok || (best.occ < 2 && c.occ >= 2)) best = c;
-            break;                                                        // deepest W ring that fits this MT
+            return c;
+        };
+        const int sw_cap = std::min(kMaxSW, env_int("HFG_TC_PAIR_SW", kMaxSW));
+        if (fixed + 2 * stage > (size_t)kTcSmemLimit) continue;
+        const int sw_max = (int)std::min<size_t>(sw_cap, ((size_t)kTcSmemLimit - fixed) / stage);
+        PairGeom c = make(sw_max);
+        if (512 / ncols >= 2) {                          // a second CTA could share the SM: largest sw that keeps it
+            const size_t half_budget = (227 * 1024) / 2 - 1024;
+            if (fixed + 2 * stage <= half_budget) {
+                const int sw2 = (int)std::min<size_t>(sw_cap, (half_budget - fixed) / stage);
+                c = make(std::max(2, sw2));
+            }
         }
+        if (!best.ok || (best.occ < 2 && c.occ >= 2)) best = c;
         if (best.ok && best.occ >= 2) break;
     }
     (void)h;
@@ -289,24 +328,44 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
     const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
-    static int regs_cache[2][2] = {{0, 0}, {0, 0}};
-    int& regs = regs_cache[BF16 ? 1 : 0][two ? 1 : 0];
+    const int ctas = g.ctas;
+    if (ctas == 2) {
+        a.w1 = reinterpret_cast<const uint8_t*>(BF16 ? P.c1.tc.w_bf16_h2 : P.c1.tc.w_tf32_h2);
+        a.w2 = reinterpret_cast<const uint8_t*>(BF16 ? P.c2.tc.w_bf16_h2 : P.c2.tc.w_tf32_h2);
+        a.w_half_stride = BF16 ? P.c1.tc.h2_stride_bf16 : P.c1.tc.h2_stride_tf32;
+    }
+    using KernelFn = void (*)(TcPairArgs);
+    KernelFn fn = nullptr;
+    if (ctas == 2) fn = two ? tc_pair_kernel<BF16, 2, 2> : tc_pair_kernel<BF16, 1, 2>;
+    else fn = two ? tc_pair_kernel<BF16, 2, 1> : tc_pair_kernel<BF16, 1, 1>;
+    // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
+    static int regs_cache[2][2][2] = {};
+    int& regs = regs_cache[BF16 ? 1 : 0][two ? 1 : 0][ctas - 1];
     if (regs == 0) {
         cudaFuncAttributes fa{};
-        if (two) check_cuda(cudaFuncGetAttributes(&fa, tc_pair_kernel<BF16, 2>), "cudaFuncGetAttributes");
-        else check_cuda(cudaFuncGetAttributes(&fa, tc_pair_kernel<BF16, 1>), "cudaFuncGetAttributes");
+        check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
         regs = std::max(1, fa.numRegs);
     }
     const int occ_regs = 65536 / (((regs + 7) / 8 * 8) * kPairThreads);
     const int occ = std::max(1, std::min(occ_regs, g.occ));
-    const int grid = std::min(a.n_tiles, h->sm_count * occ);
+    const int n_sched = (a.n_tiles + ctas - 1) / ctas;
+    const int grid = ctas * std::min(n_sched, (h->sm_count / ctas) * occ);
     const double C = a.N;
     const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
     const double bytes = (double)B * T * C * ESZ * (out ? 2 : 1) +
                          (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     h->prof_begin(st, label, flops, bytes);
-    if (two) tc_pair_kernel<BF16, 2><<<grid, kPairThreads, g.smem, st>>>(a);
-    else tc_pair_kernel<BF16, 1><<<grid, kPairThreads, g.smem, st>>>(a);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPairThreads);
+    cfg.dynamicSmemBytes = g.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    check_cuda(cudaLaunchKernelEx(&cfg, fn, a), "tc_pair_kernel launch");
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
 }
@@ -420,7 +479,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                 // destination of this pair: ping-pong between R and H; the last pair feeds the MRF sum / Y
                 const TcPlane* dst = last ? ((mode == TC_ACC_WRITE || mode == TC_ACC_ADD) ? nullptr : &S.Y)
                                           : (r == &S.R ? &S.H : &S.R);
-                const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks);
+                const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, BF16);
                 if (g.ok) {
                     tc_launch_pair<BF16>(h, st, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
                                          dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
@@ -483,7 +542,7 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     h->profiling = false;
     cudaEvent_t e0, e1;
     check_cuda(cudaEventCreate(&e0), "event"); check_cuda(cudaEventCreate(&e1), "event");
-    const PairGeom g = tc_pair_geometry(h, P, in.nchunks);
+    const PairGeom g = tc_pair_geometry(h, P, in.nchunks, BF16);
     if (which == 2 && !g.ok) throw StatusError(HFG_ERR_UNSUPPORTED, "fused pair does not fit for this layer");
     auto launch = [&]() {
         if (which == 2)
@@ -522,10 +581,13 @@ inline void configure_kernels(hfg_handle*) {
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     check_cuda(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_pair_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    auto big = [](auto fn) {
+        check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
+    };
+    big(tc_pair_kernel<true, 1, 1>); big(tc_pair_kernel<false, 1, 1>);
+    big(tc_pair_kernel<true, 2, 1>); big(tc_pair_kernel<false, 2, 1>);
+    big(tc_pair_kernel<true, 1, 2>); big(tc_pair_kernel<false, 1, 2>);
+    big(tc_pair_kernel<true, 2, 2>); big(tc_pair_kernel<false, 2, 2>);
 }
 
 }  // namespace hfg
