@@ -459,87 +459,69 @@ tc_conv_kernel(const TcConvArgs a) {
         __syncwarp();
     } else {
         // ===================== epilogue: TMEM -> regs -> global =====================
+        // 32 columns per step: both TMEM loads, the residual cells and the MRF partial sums are all
+        // issued before the first use, so one step pays one memory latency instead of one per 16 bytes.
         mbar_wait(ACC_FULL, 0);
         tc_fence_after();
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
         const int qlane = quarter * 32 + lane;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        const bool add_prev = a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL;
+        const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         for (int mt = 0; mt < MT; ++mt) {
             const int q = q0 + mt * 128 + qlane;
             const int t = q * a.out_stride + phase + a.out_off;
             const bool valid = (q < a.n_q) && (t >= 0) && (t < a.T_out);
             const long long row_bytes = (long long)(kPadL + t) * 16;
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * N + c0), r);
+            const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * N);
+            const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
+            uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+            uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                const bool two = c0 + 16 < N;
+                uint32_t r0[16], r1[16];
+                tmem_ld16(tbase + (uint32_t)c0, r0);
+                if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
+                float x0[16], x1[16], p0[16], p1[16];
+                const int ch0 = ntile * N + c0;             // first output channel of this step
+                if (valid && a.res) {
+                    load_cells16<BF16>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
+                    if (two) load_cells16<BF16>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
+                }
+                if (valid && add_prev) {
+                    load_f32x16(ap + (long long)(ch0 / 4) * a.acc_pstride, a.acc_pstride, p0);
+                    if (two) load_f32x16(ap + (long long)((ch0 + 16) / 4) * a.acc_pstride, a.acc_pstride, p1);
+                }
                 tmem_ld_wait();
                 if (!valid) continue;
-                float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sBias[c0 + i];
-                const int ch0 = ntile * N + c0;             // first output channel of this group
-                if (a.res) {                                 // x + xt   (reference :85)
-                    const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
-                    if constexpr (BF16) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    if (hh == 1 && !two) break;
+                    const int cc = c0 + 16 * hh, ch = ch0 + 16 * hh;
+                    float v[16];
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(rp + (long long)(ch0 / CW + g) * a.o_pstride);
-                            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(hh ? r1[i] : r0[i]);
+                    add_bias16(v, sBias + cc);
+                    if (a.res) {                             // x + xt   (reference :85)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                float lo, hi;
-                                unpack_bf16(w4[i], lo, hi);
-                                v[g * 8 + 2 * i] += lrelu_inv(lo, inv_slope);
-                                v[g * 8 + 2 * i + 1] += lrelu_inv(hi, inv_slope);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const float4 u = *reinterpret_cast<const float4*>(rp + (long long)(ch0 / CW + g) * a.o_pstride);
-                            v[g * 4 + 0] += lrelu_inv(u.x, inv_slope);
-                            v[g * 4 + 1] += lrelu_inv(u.y, inv_slope);
-                            v[g * 4 + 2] += lrelu_inv(u.z, inv_slope);
-                            v[g * 4 + 3] += lrelu_inv(u.w, inv_slope);
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] += lrelu_inv(hh ? x1[i] : x0[i], inv_slope);
                     }
-                }
-                if (a.acc_mode != TC_ACC_NONE) {             // MRF sum (reference :126-131)
-                    uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+                    if (add_prev) {                          // output + rb(x)  (reference :129)
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float4* cell = reinterpret_cast<float4*>(ap + (long long)(ch0 / 4 + g) * a.acc_pstride);
-                        if (a.acc_mode != TC_ACC_WRITE) {
-                            const float4 u = *cell;
-                            v[g * 4 + 0] += u.x; v[g * 4 + 1] += u.y; v[g * 4 + 2] += u.z; v[g * 4 + 3] += u.w;
-                        }
-                        if (a.acc_mode != TC_ACC_FINAL)
-                            *cell = make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        for (int i = 0; i < 16; ++i) v[i] += hh ? p1[i] : p0[i];
                     }
-                    if (a.acc_mode == TC_ACC_FINAL) {
+                    if (acc_store) {
+                        store_f32x16(ap + (long long)(ch / 4) * a.acc_pstride, a.acc_pstride, v);
+                        if (!a.out) continue;
+                    }
+                    if (a.acc_mode == TC_ACC_FINAL) {        // / len(resblocks)  (reference :131)
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
                     }
-                }
-                if (a.out) {                                 // next layer's leaky_relu, operand dtype
-                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                    if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                    if constexpr (BF16) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint4 u;
-                            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                            u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                            u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                            *reinterpret_cast<uint4*>(op + (long long)(ch0 / CW + g) * a.o_pstride) = u;
-                        }
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            *reinterpret_cast<float4*>(op + (long long)(ch0 / CW + g) * a.o_pstride) =
-                                make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                        store_cells16<BF16>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
                     }
                 }
             }
