@@ -103,6 +103,15 @@ int hfg_forward(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t fram
                 float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
                 void* stream);
 
+/* The acoustic model upstream emits mel_pred as [B, Tfrm, n_mels] (reference
+ * models/acoustic_model.py:181-265; the reference design transposes it first,
+ * .kiro/specs/tts-sam-bert-hifigan/design.md:905-906).  layout = HFG_MEL_FRAMES_LAST makes every
+ * following hfg_forward* call on this handle read that layout directly (the transpose is folded
+ * into the first kernel's load); HFG_MEL_CHANNELS_FIRST (default) is the reference's [B, n_mels, Tfrm]. */
+#define HFG_MEL_CHANNELS_FIRST 0
+#define HFG_MEL_FRAMES_LAST 1
+int hfg_set_mel_layout(hfg_handle* h, int32_t layout);
+
 /* Same, and also copies the 2*num_upsamples+1 stage-boundary activations
  * (conv_pre, then ups[i], mrfs[i] outputs; fp32 [B,C,T] device buffers; NULL
  * entries are skipped) -- what forward hooks on the reference module observe.

@@ -241,3 +241,32 @@ def test_geometry_outside_umma_shapes_falls_back_to_fp32_kernels():
     assert gen.mode == "fp32" and gen.last_launch_count > 0
     assert wav.shape == ref.shape
     assert float(np.abs(wav - ref).max()) <= 2e-5
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_config5_acoustic_model_output_feeds_generator(mode):
+    """BASELINE.json configs[4]: mel_pred [B, Tfrm, 80] produced by the UNMODIFIED reference SAM-BERT
+    acoustic model (tests/golden/make_config5.py) -> new generator.  The integer frame indexing
+    (duration rounding + repeat_interleave, reference models/variance_adaptor.py:232,746-748) is the
+    reference's own and is checked through the fixture: Tfrm == max over utterances of sum(dur)."""
+    import oracle
+    fx = load_golden("config5_acoustic_b8")
+    mel_pred, dur = fx["mel_pred"], fx["dur"]
+    assert mel_pred.shape[0] == dur.shape[0] == 8 and mel_pred.shape[2] == 80
+    assert dur.dtype == np.int64 and dur.min() >= 1                   # clamp(min=1), :748
+    assert mel_pred.shape[1] == int(dur.sum(axis=1).max())            # zero-padded to the longest, :240-260
+    cfg = synth.DEFAULT_CONFIG
+    sd = synth.make_weights(cfg, 0)
+    gen = make_gen(cfg, sd, mode)
+    x = torch.from_numpy(mel_pred).to("cuda:0")
+    with torch.no_grad():
+        a = gen.forward_frames_last(x)                                # reads [B, T, 80] directly
+        b = gen(x.transpose(1, 2).contiguous())                       # reference glue (design.md:905-906)
+    torch.cuda.synchronize()
+    assert a.shape == (8, 1, mel_pred.shape[1] * 256)
+    assert torch.equal(a, b)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()},
+                               torch.from_numpy(mel_pred).transpose(1, 2).contiguous()).numpy()
+    err = float(np.abs(a.cpu().numpy() - ref).max())
+    print(f"config5[{mode}] Tfrm {mel_pred.shape[1]} max-abs {err:.3e} peak {np.abs(ref).max():.3e}")
+    assert err <= TOL[mode] * (4 if mode == "bf16" else 1)

@@ -16,7 +16,7 @@ SYMBOLS = [
     "hfg_abi_version", "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_weight",
     "hfg_commit_weights", "hfg_out_len", "hfg_workspace_bytes", "hfg_forward",
     "hfg_forward_stages", "hfg_forward_host", "hfg_forward_host_ex", "hfg_last_launch_count",
-    "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer",
+    "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer", "hfg_set_mel_layout",
 ]
 
 
@@ -93,6 +93,8 @@ def load():
     lib.hfg_set_profiling.argtypes = [vp, i32]
     lib.hfg_get_profile.restype = ctypes.c_int
     lib.hfg_get_profile.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+    lib.hfg_set_mel_layout.restype = ctypes.c_int
+    lib.hfg_set_mel_layout.argtypes = [vp, i32]
     lib.hfg_bench_layer.restype = ctypes.c_int
     lib.hfg_bench_layer.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, fp]
     del fp
@@ -185,6 +187,9 @@ class Handle:
                      mel_pinned: bool = False, wav_pinned: bool = False):
         flags = (1 if mel_pinned else 0) | (2 if wav_pinned else 0)
         self._check(self._lib.hfg_forward_host_ex(self._h, mel_ptr, batch, frames, wav_ptr, mode, flags))
+
+    def set_mel_layout(self, frames_last: bool):
+        self._check(self._lib.hfg_set_mel_layout(self._h, 1 if frames_last else 0))
 
     def set_profiling(self, on: bool):
         self._check(self._lib.hfg_set_profiling(self._h, 1 if on else 0))

@@ -182,4 +182,19 @@ conv_post_tanh_fp32(const PostArgs a) {
     a.y[(size_t)b * a.T + t] = tanhf(acc + a.bias[0]);
 }
 
+// [B, T, C] -> [B, C, T] (fp32 mode only: the acoustic model's frames-last mel)
+__global__ void transpose_btc_to_bct(const float* __restrict__ x, float* __restrict__ y, int C, int T) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int t = t0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (t < T && c < C) ? x[((size_t)b * T + t) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, t = t0 + threadIdx.x;
+        if (c < C && t < T) y[((size_t)b * C + c) * T + t] = tile[threadIdx.x][i];
+    }
+}
+
 }  // namespace hfg

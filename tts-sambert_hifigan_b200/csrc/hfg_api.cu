@@ -249,6 +249,14 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
     };
 
     // conv_pre (reference :238), no activation on the mel
+    if (h->mel_layout == HFG_MEL_FRAMES_LAST) {           // acoustic-model layout: transpose into bufX first
+        dim3 tgrid((T + 31) / 32, (h->cfg.n_mels + 31) / 32, B);
+        h->prof_begin(st, "transpose_mel", 0, 8.0 * B * h->cfg.n_mels * T);
+        transpose_btc_to_bct<<<tgrid, dim3(32, 8), 0, st>>>(mel, bufX, h->cfg.n_mels, T);
+        h->prof_end(st);
+        check_cuda(cudaGetLastError(), "transpose launch");
+        mel = bufX;
+    }
     float* cur = bufA;
     launch_conv_fp32(h, st, conv_args(h->pre, mel, cur, T, 1.0f), h->pre.rco, T, B, "conv_pre");
     dump(0, cur, (size_t)B * C[0] * L[0]);
@@ -277,7 +285,7 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
             const float* r = bufX;
             for (size_t l = 0; l < rb.size(); ++l) {
                 const bool last = (l + 1 == rb.size());
-                const std::string lab = "mrf" + std::to_string(i);
+                const std::string lab = "mrf" + std::to_string(i) + ".k" + std::to_string(rb[l].c1.k);
                 launch_conv_fp32(h, st, conv_args(rb[l].c1, r, bufH, Tout, slope), rb[l].c1.rco, Tout, B, lab.c_str());
                 ConvArgs a2 = conv_args(rb[l].c2, bufH, last ? acc : bufR, Tout, slope);
                 a2.res = r;
@@ -524,6 +532,12 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
     check_cuda(cudaStreamSynchronize(h->stream), "stream sync");
     if (!wav_pinned) memcpy(wav_host, h->pin_wav, wav_bytes);
     HFG_CATCH(h)
+}
+
+int hfg_set_mel_layout(hfg_handle* h, int32_t layout) {
+    if (!h || (layout != HFG_MEL_CHANNELS_FIRST && layout != HFG_MEL_FRAMES_LAST)) return HFG_ERR_INVALID;
+    h->mel_layout = layout;
+    return HFG_OK;
 }
 
 int hfg_set_profiling(hfg_handle* h, int32_t enable) {

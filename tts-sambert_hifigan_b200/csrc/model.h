@@ -72,6 +72,7 @@ struct hfg_handle {
     bool committed = false;
     std::string last_error;
     int64_t launches = 0;
+    int mel_layout = 0;       // 0 = [B, n_mels, T] (reference), 1 = [B, T, n_mels] (acoustic-model output)
 
     std::map<std::string, hfg::HostTensor> sd;   // raw state_dict as set by the caller
 

@@ -539,14 +539,19 @@ tc_conv_kernel(const TcConvArgs a) {
 // mel [B, C, T] fp32 (reference layout) -> chunk planes in the operand dtype (no activation).
 template <bool BF16>
 __global__ void tc_pack_input(const float* __restrict__ x, uint8_t* __restrict__ out, int C, int T,
-                              long long bstride, long long pstride) {
+                              long long bstride, long long pstride, int frames_last) {
     constexpr int CW = BF16 ? 8 : 4;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     float v[CW];
+    if (frames_last) {                                     // x is [B, T, C]: one contiguous cell
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = x[((size_t)b * C + chunk * CW + i) * T + t];
+        for (int i = 0; i < CW; ++i) v[i] = x[((size_t)b * T + t) * C + chunk * CW + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) v[i] = x[((size_t)b * C + chunk * CW + i) * T + t];
+    }
     uint8_t* p = out + (long long)b * bstride + (long long)chunk * pstride + (long long)(kPadL + t) * 16;
     if constexpr (BF16) {
         uint4 u;

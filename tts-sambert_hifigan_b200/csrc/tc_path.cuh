@@ -399,7 +399,8 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     {
         dim3 grid((T + 127) / 128, plan.mel.nchunks, B);
         h->prof_begin(st, "pack_mel", 0, (double)B * h->cfg.n_mels * T * (4 + ESZ));
-        tc_pack_input<BF16><<<grid, 128, 0, st>>>(mel, ptr(plan.mel), h->cfg.n_mels, T, plan.mel.bstride, plan.mel.pstride);
+        tc_pack_input<BF16><<<grid, 128, 0, st>>>(mel, ptr(plan.mel), h->cfg.n_mels, T, plan.mel.bstride, plan.mel.pstride,
+                                                  h->mel_layout);
         h->prof_end(st);
         check_cuda(cudaGetLastError(), "tc_pack_input launch");
     }
@@ -468,9 +469,9 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         dump(1 + 2 * (int)i, S.X);
 
         // MRF (reference :116-131)
-        const std::string lab = "mrf" + std::to_string(i);
         for (int j = 0; j < n_rb; ++j) {
             const auto& rb = h->mrfs[i][j];
+            const std::string lab = "mrf" + std::to_string(i) + ".k" + std::to_string(rb[0].c1.k);
             const TcPlane* r = &S.X;
             for (size_t l = 0; l < rb.size(); ++l) {
                 const bool last = (l + 1 == rb.size());

@@ -227,6 +227,20 @@ class HiFiGANGenerator(nn.Module):
                 "the B200 generator is inference-only: call it under torch.no_grad() "
                 "(no autograd through the CUDA path)")
 
+    def forward_frames_last(self, mel_pred: torch.Tensor) -> torch.Tensor:
+        """mel_pred [B, Tfrm, n_mels] -- the layout SAMBERTAcousticModel.forward returns (reference
+        models/acoustic_model.py:181-265) -- to wav [B, 1, T_wav].  Equivalent to
+        forward(mel_pred.transpose(1, 2)) (reference design.md:905-906) without the transpose copy:
+        the first kernel reads the frames-last layout directly."""
+        if mel_pred.dim() != 3 or mel_pred.shape[2] != self.n_mels:
+            raise RuntimeError(f"expected mel_pred of shape [B, Tfrm, {self.n_mels}], got {list(mel_pred.shape)}")
+        self._frames_last = True
+        try:
+            # shape checks / dispatch work on the logical [B, n_mels, T] view; the buffer stays [B, T, C]
+            return self.forward(mel_pred.contiguous().transpose(1, 2))
+        finally:
+            self._frames_last = False
+
     def forward(self, mel: torch.Tensor, _stages: Optional[list] = None) -> torch.Tensor:
         """Generate waveform from mel-spectrogram (reference models/hifigan.py:224-261).
 
@@ -263,15 +277,21 @@ class HiFiGANGenerator(nn.Module):
         return wav
 
     def _dispatch(self, mel, shapes, mode, stages):
+        if getattr(self, "_frames_last", False):
+            buf = mel.transpose(1, 2)                   # back to the caller's contiguous [B, T, C] buffer
+            assert buf.is_contiguous()
+        else:
+            buf = mel.contiguous()
         if mel.is_cuda:
-            return self._forward_cuda(mel.contiguous(), shapes, mode, stages)
-        return self._forward_host(mel.contiguous(), shapes, mode)
+            return self._forward_cuda(buf, shapes, mode, stages, mel.shape)
+        return self._forward_host(buf, shapes, mode, mel.shape)
 
-    def _forward_cuda(self, mel, shapes, mode, stages):
+    def _forward_cuda(self, mel, shapes, mode, stages, logical_shape):
         dev = mel.device
-        B, _, T = mel.shape
+        B, _, T = logical_shape
         with torch.cuda.device(dev):
             h = self._handle_for(dev)
+            h.set_mel_layout(getattr(self, "_frames_last", False))
             need = h.workspace_bytes(B, T, mode)
             ws = self._workspaces.get(dev.index)
             if ws is None or ws.numel() < need:
@@ -289,10 +309,11 @@ class HiFiGANGenerator(nn.Module):
             self.last_launch_count = h.last_launch_count()
         return wav
 
-    def _forward_host(self, mel, shapes, mode):
+    def _forward_host(self, mel, shapes, mode, logical_shape):
         dev = torch.device("cuda", torch.cuda.current_device())
-        B, _, T = mel.shape
+        B, _, T = logical_shape
         h = self._handle_for(dev)
+        h.set_mel_layout(getattr(self, "_frames_last", False))
         # the result is written by DMA straight into a page-locked tensor (torch caches these)
         wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32, pin_memory=True)
         h.forward_host(mel.data_ptr(), B, T, wav.data_ptr(), mode,
