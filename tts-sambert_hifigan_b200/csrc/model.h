@@ -36,9 +36,9 @@ struct HostTensor {
 struct TcPack {
     void* w_bf16 = nullptr;   // bf16 operand tiles
     void* w_tf32 = nullptr;   // fp32 (consumed as tf32) operand tiles
-    // the same weights split into two N-halves, one per CTA of a cta_group::2 pair
-    void* w_bf16_h2 = nullptr; long long h2_stride_bf16 = 0;
-    void* w_tf32_h2 = nullptr; long long h2_stride_tf32 = 0;
+    // fused-pair kernel packs: [bf16 ? 1 : 0][N-halves for a cta_group::2 pair ? 1 : 0][K block of 4 cells ? 1 : 0]
+    void* w_pair[2][2][2] = {};
+    long long half_stride[2][2] = {};     // [bf16][kbc4]: bytes between the two N-halves
     bool ok = false;          // layer shape is covered by the tensor-core path
 };
 

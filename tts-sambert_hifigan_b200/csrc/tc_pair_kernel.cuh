@@ -51,6 +51,7 @@ struct TcPairArgs {
     int TO;           // output rows per tile = MT*128 - 2*p2
     int sa, sw;
     int tap_group;    // taps per W stage
+    int kbc;          // 16-byte cells per K block
     int tiles_per_batch, n_tiles;
     float slope;
 };
@@ -84,8 +85,9 @@ tc_pair_kernel(const TcPairArgs a) {
     const int NB = N / CTAS;                          // rows of the weight tile staged by this CTA
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const int n_chunks = a.n_chunks;
-    const int nck_max = n_chunks < 8 ? n_chunks : 8;
-    const int n_kb = (n_chunks + 7) / 8;
+    const int KBC = a.kbc;                            // 16-byte cells per K block (8, or 4 when smem is tight)
+    const int nck_max = n_chunks < KBC ? n_chunks : KBC;
+    const int n_kb = (n_chunks + KBC - 1) / KBC;
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
     const int G = a.tap_group;
     const uint32_t w_stage_bytes = (uint32_t)G * NB * nck_max * 16;
@@ -159,27 +161,27 @@ tc_pair_kernel(const TcPairArgs a) {
             return a.a + (long long)b * a.a_bstride + (long long)(kPadL + t0 - a.p2 - a.p1) * 16;
         };
         auto issue_a = [&](const uint8_t* ab, int kb) {
-            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
             mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
             if (leader) {
                 mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
                 const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
                 for (int c = 0; c < nck; ++c)
-                    bulk_g2s(dst + (uint32_t)c * R1 * 16, ab + (long long)(8 * kb + c) * a.a_pstride,
+                    bulk_g2s(dst + (uint32_t)c * R1 * 16, ab + (long long)(KBC * kb + c) * a.a_pstride,
                              (uint32_t)R1 * 16, A_FULL(sa_i));
             }
             __syncwarp();
             if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
         };
         auto issue_w = [&](const uint8_t* w, int kb, int tap0) {      // taps [tap0, tap0 + G) of K block kb
-            const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+            const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
             const int g = (k - tap0) < G ? (k - tap0) : G;
             mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
             if (leader) {
                 mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
                 bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
                          w + (long long)rank * a.w_half_stride +
-                             ((long long)kb * k * 8 + (long long)tap0 * nck) * NB * 16,
+                             ((long long)kb * k * KBC + (long long)tap0 * nck) * NB * 16,
                          (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
             }
             __syncwarp();
@@ -237,7 +239,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1 ----
             uint32_t acc_on = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 if constexpr (CTAS == 2) mbar_wait_cluster(PEER_A_FULL(sa_i), sa_ph);
@@ -274,9 +276,9 @@ tc_pair_kernel(const TcPairArgs a) {
             if constexpr (CTAS == 2) mbar_wait_cluster(H_READY, it & 1); else mbar_wait(H_READY, it & 1);
             tc_fence_after();
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
-                const uint32_t h_lo0 = h_lo_base + (uint32_t)(8 * kb * RH);
+                const uint32_t h_lo0 = h_lo_base + (uint32_t)(KBC * kb * RH);
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
@@ -321,7 +323,7 @@ tc_pair_kernel(const TcPairArgs a) {
             const int t0 = (tile % a.tiles_per_batch) * a.TO;
             // ---------- pre2: acc2 <- x + b2 (+ partial MRF sum), per K block as it lands ----------
             for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - 8 * kb) < 8 ? (n_chunks - 8 * kb) : 8;
+                const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
                 for (int mt = half; mt < MT; mt += 2) {
@@ -331,9 +333,9 @@ tc_pair_kernel(const TcPairArgs a) {
                     const uint8_t* rp = sa_p + (size_t)(lr + a.p2 + a.p1) * 16;
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
-                    const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * 8 * CW);
+                    const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * KBC * CW);
                     for (int c16 = 0; c16 < nck * CW; c16 += 16) {       // 16 columns at a time
-                        const int col = kb * 8 * CW + c16;
+                        const int col = kb * KBC * CW + c16;
                         float v[16];
                         load_cells16<BF16>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
                         float prev[16];

@@ -48,16 +48,17 @@ static inline bool tc_shape_ok(int cin, int cout) { return cin % 16 == 0 && cout
 // Layout: [phase][ntile][kb][tap][chunk(8)][n(N)][cell(CW)], cells of 16 bytes.
 template <typename F>
 static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int phases, int taps_max, F get,
-                            bool halves = false) {
-    if (!halves) {
+                            bool pair = false, bool halves = false, int kbc = 8, int only_bf = -1) {
+    if (!pair) {
         tp.ok = tc_shape_ok(cin, cout);
         if (!tp.ok) return;
     }
     // halves: two N/2-wide tiles (one per CTA of a pair) in the same [ntile][kb][tap][chunk][n] layout
-    const int N = halves ? cout / 2 : tc_pick_n(cout), ntiles = cout / N;
+    const int N = halves ? cout / 2 : (pair ? cout : tc_pick_n(cout)), ntiles = cout / N;
     for (int bf = 0; bf < 2; ++bf) {
+        if (only_bf >= 0 && bf != only_bf) continue;
         const int CW = bf ? 8 : 4;
-        const int nchunks = cin / CW, nkb = (nchunks + 7) / 8;
+        const int nchunks = cin / CW, nkb = (nchunks + kbc - 1) / kbc;
         // tight layout: [phase][ntile][kb][tap][chunk < nck(kb)][n][cell]
         const size_t per_tile = (size_t)nchunks * N * 16 * taps_max;
         const size_t total = (size_t)phases * ntiles * per_tile;
@@ -65,15 +66,15 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
         for (int ph = 0; ph < phases; ++ph)
             for (int nt = 0; nt < ntiles; ++nt)
                 for (int kb = 0; kb < nkb; ++kb) {
-                    const int nck = std::min(8, nchunks - 8 * kb);
+                    const int nck = std::min(kbc, nchunks - kbc * kb);
                     for (int tap = 0; tap < taps_max; ++tap) {
                         uint8_t* blk = buf.data() + ((size_t)ph * ntiles + nt) * per_tile +
-                                       ((size_t)kb * taps_max * 8 + (size_t)tap * nck) * N * 16;
+                                       ((size_t)kb * taps_max * kbc + (size_t)tap * nck) * N * 16;
                         for (int c = 0; c < nck; ++c)
                             for (int n = 0; n < N; ++n) {
                                 uint8_t* cell = blk + ((size_t)c * N + n) * 16;
                                 for (int e = 0; e < CW; ++e) {
-                                    const int ci = (8 * kb + c) * CW + e;
+                                    const int ci = (kbc * kb + c) * CW + e;
                                     const float v = get(nt * N + n, ci, ph, tap);
                                     if (bf) {
                                         const uint16_t q = f2bf(v);
@@ -87,9 +88,9 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
                     }
                 }
         void* d = h->upload(buf);
-        if (halves) {
-            if (bf) { tp.w_bf16_h2 = d; tp.h2_stride_bf16 = (long long)per_tile; }
-            else { tp.w_tf32_h2 = d; tp.h2_stride_tf32 = (long long)per_tile; }
+        if (pair) {
+            tp.w_pair[bf][halves ? 1 : 0][kbc == 4 ? 1 : 0] = d;
+            if (halves) tp.half_stride[bf][kbc == 4 ? 1 : 0] = (long long)per_tile;
         } else {
             if (bf) tp.w_bf16 = d; else tp.w_tf32 = d;
         }
@@ -102,9 +103,19 @@ inline void tc_pack_conv(hfg_handle* h, ConvLayer& L, const HostTensor& w, const
         return w.data[((size_t)n * cin + ci) * k + tap];                // Conv1d weight [C_out, C_in, k]
     };
     tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get);
-    // CTA-pair layout for the fused ResBlock kernel (square convs, N <= 256, N/2 a UMMA-legal half)
-    if (L.tc.ok && L.cin == L.cout && L.cout <= 256 && L.cout % 32 == 0)
-        tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, /*halves=*/true);
+    if (!L.tc.ok || L.cin != L.cout || L.cout > 256) return;
+    // packs of the fused ResBlock kernel: whole-N (one CTA) and N-halves (cta_group::2 pair), K blocks of
+    // 8 cells; tf32 additionally with K blocks of 4 cells (the fp32 H tile leaves less room for A stages)
+    const bool can_halve = L.cout % 32 == 0;
+    L.tc.w_pair[1][0][0] = L.tc.w_bf16;
+    L.tc.w_pair[0][0][0] = L.tc.w_tf32;
+    if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 8);
+    // K blocks of 4 cells let tf32 C=128 run MT=2 tiles, but measured slower than MT=1 with K blocks of 8
+    // (profiles/r1_tuning.md): packed only on request (HFG_TC_PACK_KBC4=1, tuning experiments)
+    if (L.cin / 4 >= 16 && env_int("HFG_TC_PACK_KBC4", 0)) {
+        tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, false, 4, /*only tf32*/ 0);
+        if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 4, 0);
+    }
 }
 inline void tc_pack_up(hfg_handle* h, UpLayer& L, const HostTensor& w, const HostTensor&) {
     const int cout = L.cout, k = L.k, u = L.u;
@@ -237,7 +248,7 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
 }
 
 // ---- fused ResBlock pair ----
-struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas; size_t smem; int occ; bool ok; };
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; };
 
 static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
     // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
@@ -246,7 +257,7 @@ static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
     const int N = P.c1.cout;
     const int dflt = (N >= 64 && N <= 128 && (P.c1.k >= 5 || !bf16)) ? 2 : 1;
     const int want = env_int("HFG_TC_PAIR_CTAS", dflt);
-    return (want == 2 && P.c1.tc.w_bf16_h2 && P.c2.tc.w_bf16_h2) ? 2 : 1;
+    return (want == 2 && P.c1.tc.w_pair[bf16 ? 1 : 0][1][0] && P.c2.tc.w_pair[bf16 ? 1 : 0][1][0]) ? 2 : 1;
 }
 
 static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, bool bf16) {
@@ -256,17 +267,21 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     if (env_int("HFG_TC_FUSE", 1) == 0) return g;
     if (N > env_int("HFG_TC_FUSE_MAXC", 256) || N % 16 != 0 || P.c1.cin != N || P.c2.cin != N || P.c2.cout != N) return g;
     if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
-    const int nck_max = std::min(8, n_chunks), n_kb = (n_chunks + 7) / 8;
     const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
     const int ctas = tc_pair_ctas(P, bf16);
     const int NB = N / ctas;                                              // weight rows staged per CTA
     // Candidates from the largest tile down.  Measured rule (profiles/r1_tuning.md): two co-resident
     // CTAs per SM beat one CTA with a larger tile (one CTA's epilogue hides behind the other's MMAs),
-    // so take the largest MT that still allows 2 CTAs/SM, else the largest MT that fits.
+    // so take the largest MT that still allows 2 CTAs/SM, else the largest MT that fits.  K blocks of 4
+    // cells (where packed) are tried after 8: they halve the A stages and let a larger MT fit.
     PairGeom best{};
     best.ok = false;
     for (int MT : {4, 2, 1}) {
         if (MT > mt_cap || 2 * MT * N > 512) continue;
+      for (int kbc : {8, 4}) {
+        if (!P.c1.tc.w_pair[bf16 ? 1 : 0][ctas - 1][kbc == 4 ? 1 : 0]) continue;
+        if (kbc == 4 && env_int("HFG_TC_PAIR_NO_KBC4", 0)) continue;
+        const int nck_max = std::min(kbc, n_chunks), n_kb = (n_chunks + kbc - 1) / kbc;
         // W ring: as deep as shared memory allows (<= 8 stages).  The refill loop of a stage is
         // "MMA done -> commit -> producer -> L2 -> smem (-> peer forward)", about 1-2 us, so the ring must
         // hold that much MMA work; when a second CTA can share the SM, stop at the depth that keeps it.
@@ -280,7 +295,7 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         while (ncols < 2 * MT * N) ncols <<= 1;
         auto make = [&](int sw) {
             PairGeom c{};
-            c.ctas = ctas;
+            c.ctas = ctas; c.kbc = kbc;
             c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2;
             c.smem = fixed + (size_t)sw * stage;
             c.occ = std::max(1, std::min((int)((227 * 1024) / (c.smem + 1024)), 512 / ncols));
@@ -299,6 +314,8 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
             }
         }
         if (!best.ok || (best.occ < 2 && c.occ >= 2)) best = c;
+        break;                                           // this MT fits with this K block: no need for the smaller one
+      }
         if (best.ok && best.occ >= 2) break;
     }
     (void)h;
@@ -314,8 +331,11 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     constexpr int ESZ = BF16 ? 2 : 4;
     TcPairArgs a{};
     a.a = in; a.a_bstride = in_b; a.a_pstride = in_p;
-    a.w1 = reinterpret_cast<const uint8_t*>(BF16 ? P.c1.tc.w_bf16 : P.c1.tc.w_tf32);
-    a.w2 = reinterpret_cast<const uint8_t*>(BF16 ? P.c2.tc.w_bf16 : P.c2.tc.w_tf32);
+    const int vb = BF16 ? 1 : 0, vk = g.kbc == 4 ? 1 : 0;
+    a.w1 = reinterpret_cast<const uint8_t*>(P.c1.tc.w_pair[vb][g.ctas - 1][vk]);
+    a.w2 = reinterpret_cast<const uint8_t*>(P.c2.tc.w_pair[vb][g.ctas - 1][vk]);
+    a.w_half_stride = P.c1.tc.half_stride[vb][vk];
+    a.kbc = g.kbc;
     a.b1 = P.c1.bias; a.b2 = P.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
@@ -329,11 +349,6 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
     const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
     const int ctas = g.ctas;
-    if (ctas == 2) {
-        a.w1 = reinterpret_cast<const uint8_t*>(BF16 ? P.c1.tc.w_bf16_h2 : P.c1.tc.w_tf32_h2);
-        a.w2 = reinterpret_cast<const uint8_t*>(BF16 ? P.c2.tc.w_bf16_h2 : P.c2.tc.w_tf32_h2);
-        a.w_half_stride = BF16 ? P.c1.tc.h2_stride_bf16 : P.c1.tc.h2_stride_tf32;
-    }
     using KernelFn = void (*)(TcPairArgs);
     KernelFn fn = nullptr;
     if (ctas == 2) fn = two ? tc_pair_kernel<BF16, 2, 2> : tc_pair_kernel<BF16, 1, 2>;
