@@ -12,6 +12,11 @@
 
 namespace hfg {
 
+static inline int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+
 // --------------------------------------------------------------------------
 // operand packing
 // --------------------------------------------------------------------------
@@ -201,10 +206,6 @@ inline size_t tc_workspace_bytes(const hfg_handle* h, int B, int T, int mode) {
 // --------------------------------------------------------------------------
 constexpr int kTcSmemLimit = 220 * 1024;
 
-static inline int env_int(const char* name, int dflt) {
-    const char* s = getenv(name);
-    return s ? atoi(s) : dflt;
-}
 
 // taps per W stage: aim at >= 16 KB per bulk copy so tiny layers do not drown in barrier round trips
 static inline int tc_tap_group(int N, int nck_max, int taps) {
