@@ -152,6 +152,21 @@ int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed);
 int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair, int32_t which,
                     int32_t batch, int32_t rows, int32_t mode, int32_t iters, float* ms);
 
+/* ---- upstream glue: integer frame indexing of the acoustic model ----
+ * Stand-alone (no handle); asynchronous on `stream`; all pointers are device pointers.
+ *
+ * hfg_durations_from_log: dur = clamp(round_half_even(exp(log_dur)), min=1) as int64
+ *   (VarianceAdaptor inference branch, reference models/variance_adaptor.py:746-748).
+ * hfg_length_regulate: LengthRegulator.forward (reference models/variance_adaptor.py:171-269):
+ *   out[b, t, :] = henc[b, p(t), :] (repeat_interleave by clamp(dur, min=0)), zeros for
+ *   t >= sum(dur[b]); out is [B, Tfrm, D] with Tfrm chosen by the caller (the reference uses the
+ *   batch maximum, which hfg_length_regulate_frames computes -- that call synchronises `stream`). */
+int hfg_durations_from_log(const float* log_dur, int64_t n, int64_t* dur, void* stream);
+int hfg_length_regulate_frames(const int64_t* dur, int32_t batch, int32_t n_phonemes, int64_t* max_frames,
+                               void* stream);
+int hfg_length_regulate(const float* henc, const int64_t* dur, int32_t batch, int32_t n_phonemes,
+                        int32_t d_model, int32_t frames, float* out, void* stream);
+
 /* Number of kernels the last hfg_forward* call on this handle launched. */
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches);
 

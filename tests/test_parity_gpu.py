@@ -270,3 +270,22 @@ def test_config5_acoustic_model_output_feeds_generator(mode):
     err = float(np.abs(a.cpu().numpy() - ref).max())
     print(f"config5[{mode}] Tfrm {mel_pred.shape[1]} max-abs {err:.3e} peak {np.abs(ref).max():.3e}")
     assert err <= TOL[mode] * (4 if mode == "bf16" else 1)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_ragged_batch_valid_region_is_identical(mode):
+    """a per-utterance length vector lets the path skip padded frames; the
+    valid region of every utterance must equal the reference-style full-length run bit for bit."""
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 6), mode)
+    lens = [169, 297, 393, 214, 40, 185, 323, 1]                      # config-5-like raggedness
+    mel = torch.from_numpy(synth.make_mel(13, len(lens), 80, max(lens))).to("cuda:0")
+    with torch.no_grad():
+        full = gen(mel)                                               # what the reference does: no masks
+        rag = gen.forward_ragged(mel, lens)
+    torch.cuda.synchronize()
+    assert rag.shape == full.shape
+    for i, n in enumerate(lens):
+        assert torch.equal(rag[i, :, : n * 256], full[i, :, : n * 256]), i
+    with pytest.raises(RuntimeError):
+        gen.forward_ragged(mel, lens[:-1])

@@ -5,5 +5,6 @@ include/hfg.h."""
 from . import synth  # noqa: F401
 from . import _capi  # noqa: F401
 from .generator import HiFiGANGenerator  # noqa: F401
+from .length_regulator import LengthRegulator, durations_from_log  # noqa: F401
 
-__all__ = ["HiFiGANGenerator", "synth"]
+__all__ = ["HiFiGANGenerator", "LengthRegulator", "durations_from_log", "synth"]

@@ -17,6 +17,7 @@ SYMBOLS = [
     "hfg_commit_weights", "hfg_out_len", "hfg_workspace_bytes", "hfg_forward",
     "hfg_forward_stages", "hfg_forward_host", "hfg_forward_host_ex", "hfg_last_launch_count",
     "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer", "hfg_set_mel_layout",
+    "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
 ]
 
 
@@ -95,6 +96,12 @@ def load():
     lib.hfg_get_profile.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
     lib.hfg_set_mel_layout.restype = ctypes.c_int
     lib.hfg_set_mel_layout.argtypes = [vp, i32]
+    lib.hfg_durations_from_log.restype = ctypes.c_int
+    lib.hfg_durations_from_log.argtypes = [vp, ctypes.c_int64, vp, vp]
+    lib.hfg_length_regulate_frames.restype = ctypes.c_int
+    lib.hfg_length_regulate_frames.argtypes = [vp, i32, i32, i64p, vp]
+    lib.hfg_length_regulate.restype = ctypes.c_int
+    lib.hfg_length_regulate.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
     lib.hfg_bench_layer.restype = ctypes.c_int
     lib.hfg_bench_layer.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, fp]
     del fp

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "fp32_kernels.cuh"
+#include "length_regulator.cuh"
 #include "model.h"
 #include "tc_path.cuh"
 
@@ -588,6 +589,63 @@ int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair
     else if (mode == HFG_MODE_TF32) *ms = tc_bench_layer_impl<false>(h, stage, resblock, pair, which, batch, rows, iters);
     else throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: tensor-core modes only");
     HFG_CATCH(h)
+}
+
+static int lr_fail(cudaError_t e) { (void)e; cudaGetLastError(); return HFG_ERR_CUDA; }
+
+int hfg_durations_from_log(const float* log_dur, int64_t n, int64_t* dur, void* stream) {
+    if (!log_dur || !dur || n <= 0) return HFG_ERR_INVALID;
+    lr_durations_from_log<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        log_dur, (long long)n, reinterpret_cast<long long*>(dur));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? HFG_OK : lr_fail(e);
+}
+
+// scratch for the prefix sums: [B*Tph + B] ints, stream-ordered allocation
+static int lr_scan(const int64_t* dur, int B, int Tph, cudaStream_t st, int** cum, int** totals) {
+    int* buf = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&buf, sizeof(int) * ((size_t)B * Tph + B), st);
+    if (e != cudaSuccess) return lr_fail(e);
+    *cum = buf;
+    *totals = buf + (size_t)B * Tph;
+    lr_prefix_sum<<<B, 256, 0, st>>>(reinterpret_cast<const long long*>(dur), Tph, *cum, *totals);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFreeAsync(buf, st); return lr_fail(e); }
+    return HFG_OK;
+}
+
+int hfg_length_regulate_frames(const int64_t* dur, int32_t batch, int32_t n_phonemes, int64_t* max_frames,
+                               void* stream) {
+    if (!dur || !max_frames || batch <= 0 || n_phonemes <= 0) return HFG_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int *cum = nullptr, *totals = nullptr;
+    int rc = lr_scan(dur, batch, n_phonemes, st, &cum, &totals);
+    if (rc != HFG_OK) return rc;
+    std::vector<int> host(batch);
+    cudaError_t e = cudaMemcpyAsync(host.data(), totals, sizeof(int) * batch, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFreeAsync(cum, st);
+    if (e != cudaSuccess) return lr_fail(e);
+    int64_t m = 0;
+    for (int v : host) m = std::max<int64_t>(m, v);
+    *max_frames = m;
+    return HFG_OK;
+}
+
+int hfg_length_regulate(const float* henc, const int64_t* dur, int32_t batch, int32_t n_phonemes,
+                        int32_t d_model, int32_t frames, float* out, void* stream) {
+    if (!henc || !dur || !out || batch <= 0 || n_phonemes <= 0 || d_model <= 0 || frames <= 0 || batch > 65535)
+        return HFG_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    int *cum = nullptr, *totals = nullptr;
+    int rc = lr_scan(dur, batch, n_phonemes, st, &cum, &totals);
+    if (rc != HFG_OK) return rc;
+    const int tx = d_model >= 128 ? 64 : 32, ty = 256 / tx;
+    dim3 grid((frames + ty - 1) / ty, batch);
+    lr_expand<<<grid, dim3(tx, ty), 0, st>>>(henc, cum, n_phonemes, d_model, frames, out);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(cum, st);
+    return e == cudaSuccess ? HFG_OK : lr_fail(e);
 }
 
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches) {

@@ -241,6 +241,33 @@ class HiFiGANGenerator(nn.Module):
         finally:
             self._frames_last = False
 
+    @torch.no_grad()
+    def forward_ragged(self, mel: torch.Tensor, lengths, halo: int = 14, bucket: int = 64) -> torch.Tensor:
+        """Variable-length batch: mel [B, n_mels, Tmax] zero- (or garbage-) padded, `lengths` the valid
+        frame counts.  The reference has no masks and synthesises every utterance out to the batch
+        maximum; here utterances are grouped by length and each group is generated
+        only up to its longest member + `halo` frames (the receptive radius is 13 frames, so the VALID
+        region [0, len*hop) of every utterance is bit-identical to the full-length run -- checked by
+        tests/test_parity_gpu.py::test_ragged_batch_valid_region_is_identical).  Samples beyond
+        (len + halo) * hop are returned as zeros instead of the reference's padding-driven garbage."""
+        self._check_input(mel)
+        lens = [int(x) for x in (lengths.tolist() if hasattr(lengths, "tolist") else lengths)]
+        B, _, T = mel.shape
+        if len(lens) != B or min(lens) < 1 or max(lens) > T:
+            raise RuntimeError("lengths must hold one frame count in [1, Tmax] per utterance")
+        hop = self._stage_shapes(1, 1)[-1][2]
+        if self._stage_shapes(1, 2)[-1][2] != 2 * hop:
+            raise RuntimeError("forward_ragged needs T_out == T*hop (upsample kernels with even k-u)")
+        wav = torch.zeros((B, 1, T * hop), dtype=torch.float32, device=mel.device)
+        groups = {}
+        for i, n in enumerate(lens):
+            groups.setdefault(min(T, (n + halo + bucket - 1) // bucket * bucket), []).append(i)
+        for t_run, idx in sorted(groups.items()):
+            sel = torch.as_tensor(idx, device=mel.device)
+            out = self.forward(mel.index_select(0, sel)[:, :, :t_run].contiguous())
+            wav[sel, :, : t_run * hop] = out
+        return wav
+
     def forward(self, mel: torch.Tensor, _stages: Optional[list] = None) -> torch.Tensor:
         """Generate waveform from mel-spectrogram (reference models/hifigan.py:224-261).
 
