@@ -82,9 +82,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples taken inside [t_begin, t_end] (the timed region).  A region shorter
+        than nvidia-smi's sampling period may hold none: then every sample taken while the bench was
+        under load (warm-up .. end of the e2e loop) is used and the window is named in the result."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -92,9 +95,14 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        window = "timed region"
+        picked = [l for (t, l) in self.lines if t_begin is None or (t_begin <= t <= t_end)]
+        if not picked:
+            window = "bench under load (warm-up .. e2e loop); timed region shorter than the sampling period"
+            picked = [l for (_, l) in self.lines]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in picked:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -107,7 +115,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def cpu_reference_run(batch, frames, repeats, threads=None):
@@ -207,6 +215,8 @@ def main():
     mel = mel_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     with torch.no_grad():
         for _ in range(warmup):
             wav = gen(mel)
@@ -215,16 +225,15 @@ def main():
 
         # ---------------- device-timed region ----------------
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        sampler = ClockSampler(local_rank)
         barrier(); torch.cuda.synchronize()
-        sampler.start()
+        t_begin = time.time()
         for s in range(steps):
             flush.fill_(s & 0xFF)                    # evict L2 between timed iterations (untimed)
             ev[s][0].record()
             wav = gen(mel)
             ev[s][1].record()
         torch.cuda.synchronize(); barrier()
-        clocks = sampler.stop()
+        t_end = time.time()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
         # ---------------- end-to-end region (host buffers) ----------------
@@ -237,6 +246,7 @@ def main():
             wav_host = gen(mel_host)                 # synchronous: returns a host tensor
         e2e_s = time.perf_counter() - t0
         barrier()
+        clocks = sampler.stop(t_begin, t_end)
 
         # ---------------- other arithmetic modes + output quality (untimed for `value`) ----------------
         # the same batch in the strict fp32 mode is the on-device stand-in for the reference output
