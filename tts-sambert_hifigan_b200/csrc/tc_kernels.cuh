@@ -37,7 +37,8 @@
 
 namespace hfg {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the column steps
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
 constexpr int kPadL = 32;          // zero rows in front of t = 0 in every plane
 constexpr int kMaxSA = 2, kMaxSW = 8;
 
@@ -371,7 +372,7 @@ tc_conv_kernel(const TcConvArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < N; i += 128) sBias[i] = a.bias[ntile * N + i];
+        for (int i = threadIdx.x - 64; i < N; i += (int)blockDim.x - 64) sBias[i] = a.bias[ntile * N + i];
     }
     tc_fence_before();
     __syncthreads();
@@ -464,6 +465,7 @@ tc_conv_kernel(const TcConvArgs a) {
         mbar_wait(ACC_FULL, 0);
         tc_fence_after();
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                   // the two warps of a quarter alternate 32-column steps
         const int qlane = quarter * 32 + lane;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
         const bool add_prev = a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL;
@@ -477,7 +479,10 @@ tc_conv_kernel(const TcConvArgs a) {
             const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
             uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
             uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
-            for (int c0 = 0; c0 < N; c0 += 32) {
+            // launched with 4 or 8 epilogue warps (blockDim 192 / 320): with 8, the two warps of a TMEM lane
+            // quarter alternate 32-column steps
+            const int col_step = 32 * (((int)blockDim.x - 64) / 128);
+            for (int c0 = 32 * half; c0 < N; c0 += col_step) {
                 const bool two = c0 + 16 < N;
                 uint32_t r0[16], r1[16];
                 tmem_ld16(tbase + (uint32_t)c0, r0);

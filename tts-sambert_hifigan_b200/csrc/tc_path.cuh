@@ -243,7 +243,10 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     const size_t smem = smem_need(MT, sa, sw);
     dim3 grid(B * a.tiles_per_batch, a.phases * (cout / a.N), 1);
     h->prof_begin(st, label, flops, bytes);
-    tc_conv_kernel<BF16><<<grid, kTcThreads, smem, st>>>(a);
+    // 8 epilogue warps when the CTA owns its SM anyway (big tiles: latency-bound epilogue, profiles/r1_tuning.md);
+    // 4 when two CTAs can share the SM (narrow layers), which hides the epilogue better than more warps
+    const int threads = (2 * (smem + 1024) <= 227 * 1024 && env_int("HFG_TC_CONV_WARPS", 0) != 8) ? 192 : kTcThreads;
+    tc_conv_kernel<BF16><<<grid, threads, smem, st>>>(a);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_conv_kernel launch");
 }
