@@ -52,6 +52,7 @@ struct TcPairArgs {
     int sa, sw;
     int tap_group;    // taps per W stage
     int kbc;          // 16-byte cells per K block
+    int poll_ns;      // producer back-off when both rings are full
     int tiles_per_batch, n_tiles;
     float slope;
 };
@@ -160,48 +161,57 @@ tc_pair_kernel(const TcPairArgs a) {
             const int t0 = (tile % a.tiles_per_batch) * a.TO;
             return a.a + (long long)b * a.a_bstride + (long long)(kPadL + t0 - a.p2 - a.p1) * 16;
         };
-        auto issue_a = [&](const uint8_t* ab, int kb) {
-            const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
-            mbar_wait(A_EMPTY(sa_i), sa_ph ^ 1);
-            if (leader) {
-                mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
-                const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
-                for (int c = 0; c < nck; ++c)
-                    bulk_g2s(dst + (uint32_t)c * R1 * 16, ab + (long long)(KBC * kb + c) * a.a_pstride,
-                             (uint32_t)R1 * 16, A_FULL(sa_i));
-            }
-            __syncwarp();
-            if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
-        };
-        auto issue_w = [&](const uint8_t* w, int kb, int tap0) {      // taps [tap0, tap0 + G) of K block kb
-            const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
-            const int g = (k - tap0) < G ? (k - tap0) : G;
-            mbar_wait(W_EMPTY(sw_i), sw_ph ^ 1);
-            if (leader) {
-                mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
-                bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
-                         w + (long long)rank * a.w_half_stride +
-                             ((long long)kb * k * KBC + (long long)tap0 * nck) * NB * 16,
-                         (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
-            }
-            __syncwarp();
-            if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-        };
-        if (sched0 < n_sched) issue_a(tile_src(tile_of(sched0)), 0);
-        for (int sc = sched0; sc < n_sched; sc += sched_step) {
-            const uint8_t* ab = tile_src(tile_of(sc));
-            const int next = sc + sched_step;
-            for (int kb = 0; kb < n_kb; ++kb)
-                for (int tap = 0; tap < k; tap += G) {
-                    issue_w(a.w1, kb, tap);
-                    if (tap == 0 && kb + 1 < n_kb) issue_a(ab, kb + 1);
+        // Two independent streams -- activation K blocks (A ring) and weight stages (W ring) -- issued by
+        // one polling thread: whichever ring has a free slot gets its next copy.  (Issuing them in one
+        // blocking program order let a full A ring stall the weight stream and starve the MMAs:
+        // profiles/r1_tuning.md section 6.)
+        const int n_my = sched0 < n_sched ? (n_sched - sched0 + sched_step - 1) / sched_step : 0;
+        const int groups = (k + G - 1) / G;
+        int a_t = 0, a_kb = 0;                                   // next A block: tile ordinal, K block
+        int w_t = 0, w_conv = 0, w_kb = 0, w_g = 0;              // next W stage
+        uint32_t idle = 0;
+        long long t_idle0 = 0;
+        while (a_t < n_my || w_t < n_my) {
+            bool did = false;
+            if (a_t < n_my && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
+                const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
+                if (leader) {
+                    const uint8_t* ab = tile_src(tile_of(sched0 + a_t * sched_step));
+                    mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
+                    const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
+                    for (int c = 0; c < nck; ++c)
+                        bulk_g2s(dst + (uint32_t)c * R1 * 16, ab + (long long)(KBC * a_kb + c) * a.a_pstride,
+                                 (uint32_t)R1 * 16, A_FULL(sa_i));
                 }
-            for (int kb = 0; kb < n_kb; ++kb)
-                for (int tap = 0; tap < k; tap += G) {
-                    issue_w(a.w2, kb, tap);
-                    // first K block of the NEXT tile: lands while conv2 of this tile still runs
-                    if (kb == 0 && tap == 0 && next < n_sched) issue_a(tile_src(tile_of(next)), 0);
+                __syncwarp();
+                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
+                if (++a_kb == n_kb) { a_kb = 0; ++a_t; }
+                did = true;
+            }
+            if (w_t < n_my && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
+                const int nck = (n_chunks - KBC * w_kb) < KBC ? (n_chunks - KBC * w_kb) : KBC;
+                const int tap0 = w_g * G;
+                const int g = (k - tap0) < G ? (k - tap0) : G;
+                if (leader) {
+                    const uint8_t* w = w_conv ? a.w2 : a.w1;
+                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
+                    bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
+                             w + (long long)rank * a.w_half_stride +
+                                 ((long long)w_kb * k * KBC + (long long)tap0 * nck) * NB * 16,
+                             (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
                 }
+                __syncwarp();
+                if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                if (++w_g == groups) { w_g = 0; if (++w_kb == n_kb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; } } }
+                did = true;
+            }
+            if (did) { idle = 0; t_idle0 = 0; continue; }
+            if (a.poll_ns > 0) __nanosleep(a.poll_ns);
+            if ((++idle & 4095u) == 0) {                         // bounded: trap instead of hanging the GPU
+                const long long now = clock64();
+                if (t_idle0 == 0) t_idle0 = now;
+                else if (now - t_idle0 > 4000000000ll) __trap();
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -307,7 +317,10 @@ tc_pair_kernel(const TcPairArgs a) {
         // ===================== epilogue warps =====================
         const int e = warp - 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int half = e >> 2;                      // the two warps of a quarter split the sub-tiles
+        const int half = e >> 2;                      // the two warps of a quarter split the sub-tiles ...
+        const bool split_cols = MT == 1;              // ... or, with a single sub-tile, alternate column steps
+        const int mt_first = split_cols ? 0 : half, mt_step = split_cols ? 1 : 2;
+        const int cs = split_cols ? 2 : 1, ch = split_cols ? half : 0;   // column-step stride / phase
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
@@ -326,7 +339,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
-                for (int mt = half; mt < MT; mt += 2) {
+                for (int mt = mt_first; mt < MT; mt += mt_step) {
                     const int lr = mt * 128 + row;                      // output row inside the tile
                     const int t = t0 + lr;
                     const bool add_prev = add_prev_mode && real && lr < a.TO && t < a.T;
@@ -334,7 +347,7 @@ tc_pair_kernel(const TcPairArgs a) {
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
                     const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * KBC * CW);
-                    for (int c16 = 0; c16 < nck * CW; c16 += 16) {       // 16 columns at a time
+                    for (int c16 = 16 * ch; c16 < nck * CW; c16 += 16 * cs) {   // 16 columns at a time
                         const int col = kb * KBC * CW + c16;
                         float v[16];
                         load_cells16<BF16>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
@@ -358,13 +371,13 @@ tc_pair_kernel(const TcPairArgs a) {
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
             mbar_wait(ACC1_FULL, it & 1);
             tc_fence_after();
-            for (int mt = half; mt < MT; mt += 2) {
+            for (int mt = mt_first; mt < MT; mt += mt_step) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
                 const float keep = (th >= 0 && th < a.T) ? 1.f : 0.f;   // conv2 zero-pads ITS input
                 uint8_t* hp = sH + (size_t)hr * 16;
                 const uint32_t tbase = acc1 + lane_sel + (uint32_t)(mt * N);
-                for (int c0 = 0; c0 < N; c0 += 32) {
+                for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
                     uint32_t r0[16], r1[16];
                     const bool two = c0 + 16 < N;
                     tmem_ld16(tbase + (uint32_t)c0, r0);
@@ -397,7 +410,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // ---------- epi2: acc2 -> global ----------
             mbar_wait(ACC2_FULL, it & 1);
             tc_fence_after();
-            for (int mt = half; mt < MT; mt += 2) {
+            for (int mt = mt_first; mt < MT; mt += mt_step) {
                 const int lr = mt * 128 + row;
                 const int t = t0 + lr;
                 const bool valid = real && lr < a.TO && t < a.T;
@@ -405,7 +418,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N);
                 uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
                 uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
-                for (int c0 = 0; c0 < N; c0 += 32) {
+                for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
                     uint32_t r0[16], r1[16];
                     const bool two = c0 + 16 < N;
                     tmem_ld16(tbase + (uint32_t)c0, r0);

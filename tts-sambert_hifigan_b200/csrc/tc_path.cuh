@@ -340,6 +340,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     a.w2 = reinterpret_cast<const uint8_t*>(P.c2.tc.w_pair[vb][g.ctas - 1][vk]);
     a.w_half_stride = P.c1.tc.half_stride[vb][vk];
     a.kbc = g.kbc;
+    a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.b1 = P.c1.bias; a.b2 = P.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
