@@ -53,6 +53,7 @@ struct TcPairArgs {
     int tap_group;    // taps per W stage
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
+    int dbg;          // timing experiments only (results are wrong): 1 = no weight copies, 2 = no activation copies
     int tiles_per_batch, n_tiles;
     float slope;
 };
@@ -105,23 +106,20 @@ tc_pair_kernel(const TcPairArgs a) {
     auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxSA + kMaxSW + i); };
     const uint32_t ACC1_FULL = bar0 + 8u * (2 * kMaxSA + 2 * kMaxSW);
     const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16;
-    auto PEER_A_FULL = [&](int i) { return ACC1_FULL + 24 + 8u * i; };            // leader only: peer's stages landed
-    auto PEER_W_FULL = [&](int i) { return ACC1_FULL + 24 + 8u * (kMaxSA + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 3 + kMaxSA + kMaxSW);
 
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * N) ncols <<= 1;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), 1); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
-        for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), 1); mbar_init(W_EMPTY(i), 1); }
+        // pair mode: the LEADER's full barriers also collect the peer's "my copy of this stage has landed"
+        // (one remote arrive), so its MMA warp waits on a single barrier per stage
+        const uint32_t full_count = (CTAS == 2 && rank == 0) ? 2u : 1u;
+        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), full_count); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
+        for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), full_count); mbar_init(W_EMPTY(i), 1); }
         mbar_init(ACC1_FULL, 1);
         mbar_init(H_READY, kPairEpiWarps * CTAS);
         mbar_init(ACC2_FULL, 1);
-        if constexpr (CTAS == 2) {
-            for (int i = 0; i < a.sa; ++i) mbar_init(PEER_A_FULL(i), 1);
-            for (int i = 0; i < a.sw; ++i) mbar_init(PEER_W_FULL(i), 1);
-        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -175,7 +173,8 @@ tc_pair_kernel(const TcPairArgs a) {
             bool did = false;
             if (a_t < n_my && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
-                if (leader) {
+                if (leader && (a.dbg & 2)) mbar_arrive(A_FULL(sa_i));
+                if (leader && !(a.dbg & 2)) {
                     const uint8_t* ab = tile_src(tile_of(sched0 + a_t * sched_step));
                     mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
                     const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
@@ -192,7 +191,8 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks - KBC * w_kb) < KBC ? (n_chunks - KBC * w_kb) : KBC;
                 const int tap0 = w_g * G;
                 const int g = (k - tap0) < G ? (k - tap0) : G;
-                if (leader) {
+                if (leader && (a.dbg & 1)) mbar_arrive(W_FULL(sw_i));
+                if (leader && !(a.dbg & 1)) {
                     const uint8_t* w = w_conv ? a.w2 : a.w1;
                     mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
@@ -230,14 +230,14 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int uses = total_w / a.sw + (lane < total_w % a.sw ? 1 : 0);
                 for (int u = 0; u < uses; ++u) {
                     mbar_wait(W_FULL(lane), (uint32_t)(u & 1));
-                    mbar_arrive_remote(PEER_W_FULL(lane), 0);
+                    mbar_arrive_remote(W_FULL(lane), 0);
                 }
             } else if (lane < a.sw + a.sa) {
                 const int sl = lane - a.sw;
                 const int uses = total_a / a.sa + (sl < total_a % a.sa ? 1 : 0);
                 for (int u = 0; u < uses; ++u) {
                     mbar_wait(A_FULL(sl), (uint32_t)(u & 1));
-                    mbar_arrive_remote(PEER_A_FULL(sl), 0);
+                    mbar_arrive_remote(A_FULL(sl), 0);
                 }
             }
             __syncwarp();
@@ -252,13 +252,11 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
                 mbar_wait(A_FULL(sa_i), sa_ph);
-                if constexpr (CTAS == 2) mbar_wait_cluster(PEER_A_FULL(sa_i), sa_ph);
                 tc_fence_after();
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
-                    if constexpr (CTAS == 2) mbar_wait_cluster(PEER_W_FULL(sw_i), sw_ph);
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
@@ -292,7 +290,6 @@ tc_pair_kernel(const TcPairArgs a) {
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
                     mbar_wait(W_FULL(sw_i), sw_ph);
-                    if constexpr (CTAS == 2) mbar_wait_cluster(PEER_W_FULL(sw_i), sw_ph);
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {

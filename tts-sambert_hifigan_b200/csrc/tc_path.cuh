@@ -12,9 +12,18 @@
 
 namespace hfg {
 
+// Tuning knobs (HFG_TC_*): read from the environment once per thread and cached by literal address,
+// so the launch path does not call getenv() hundreds of times per forward.
 static inline int env_int(const char* name, int dflt) {
+    struct Ent { const char* name; bool set; int val; };
+    thread_local Ent cache[48];
+    thread_local int n = 0;
+    for (int i = 0; i < n; ++i)
+        if (cache[i].name == name) return cache[i].set ? cache[i].val : dflt;
     const char* s = getenv(name);
-    return s ? atoi(s) : dflt;
+    Ent e{name, s != nullptr, s ? atoi(s) : 0};
+    if (n < 48) cache[n++] = e;
+    return e.set ? e.val : dflt;
 }
 
 // --------------------------------------------------------------------------
@@ -286,19 +295,27 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         if (!P.c1.tc.w_pair[bf16 ? 1 : 0][ctas - 1][kbc == 4 ? 1 : 0]) continue;
         if (kbc == 4 && env_int("HFG_TC_PAIR_NO_KBC4", 0)) continue;
         const int nck_max = std::min(kbc, n_chunks), n_kb = (n_chunks + kbc - 1) / kbc;
-        // W ring: as deep as shared memory allows (<= 8 stages).  The refill loop of a stage is
-        // "MMA done -> commit -> producer -> L2 -> smem (-> peer forward)", about 1-2 us, so the ring must
-        // hold that much MMA work; when a second CTA can share the SM, stop at the depth that keeps it.
-        const int G = tc_tap_group(NB, nck_max, k);
+        // W ring.  Measured (profiles/r1_tuning.md section 6): with the data always ready the kernel is still
+        // bound by the MMA warp's per-stage round trip (two mbarrier waits, fence, commit), so stages are made
+        // as FAT as shared memory allows -- G taps per stage with at least `sw_min` stages -- rather than deep.
+        // When a second CTA can share the SM the budget is half the SM (that co-residency is worth more).
         const int sa = std::min(kMaxSA, n_kb);
         const int R1 = MT * 128 + 2 * p1;
         const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
-        const size_t stage = (size_t)G * NB * nck_max * 16;
+        const size_t tap_bytes = (size_t)NB * nck_max * 16;
         const size_t fixed = (size_t)sa * R1 * nck_max * 16 + (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 384;
         int ncols = 32;
         while (ncols < 2 * MT * N) ncols <<= 1;
-        auto make = [&](int sw) {
+        const int sw_min = std::max(2, env_int("HFG_TC_PAIR_SWMIN", 2));
+        const size_t stage_cap = (size_t)env_int("HFG_TC_STAGE_BYTES", 65536);
+        auto make = [&](size_t budget) {
             PairGeom c{};
+            c.ok = false;
+            if (fixed + sw_min * tap_bytes > budget) return c;
+            int G = (int)std::min<size_t>((size_t)k, (budget - fixed) / (sw_min * tap_bytes));
+            G = (int)std::min<size_t>((size_t)G, std::max<size_t>(1, stage_cap / tap_bytes));
+            const size_t stage = (size_t)G * tap_bytes;
+            const int sw = (int)std::min<size_t>(kMaxSW, (budget - fixed) / stage);
             c.ctas = ctas; c.kbc = kbc;
             c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2;
             c.smem = fixed + (size_t)sw * stage;
@@ -306,16 +323,13 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
             c.ok = true;
             return c;
         };
-        const int sw_cap = std::min(kMaxSW, env_int("HFG_TC_PAIR_SW", kMaxSW));
-        if (fixed + 2 * stage > (size_t)kTcSmemLimit) continue;
-        const int sw_max = (int)std::min<size_t>(sw_cap, ((size_t)kTcSmemLimit - fixed) / stage);
-        PairGeom c = make(sw_max);
-        if (512 / ncols >= 2) {                          // a second CTA could share the SM: largest sw that keeps it
-            const size_t half_budget = (227 * 1024) / 2 - 1024;
-            if (fixed + 2 * stage <= half_budget) {
-                const int sw2 = (int)std::min<size_t>(sw_cap, (half_budget - fixed) / stage);
-                c = make(std::max(2, sw2));
-            }
+        PairGeom c = make((size_t)kTcSmemLimit);
+        if (!c.ok) continue;
+        // a second CTA could share the SM: worth more than fat stages for N <= 64 (stage 2: 63.6 vs 69.5 us,
+        // stage 3: 73.8 vs 124 us at k = 11), not for N = 128 (115.8 vs 98.6 us)
+        if (512 / ncols >= 2 && env_int("HFG_TC_PAIR_OCC2", N <= 64 ? 1 : 0)) {
+            PairGeom c2 = make((227 * 1024) / 2 - 1024);
+            if (c2.ok) c = c2;
         }
         if (!best.ok || (best.occ < 2 && c.occ >= 2)) best = c;
         break;                                           // this MT fits with this K block: no need for the smaller one
@@ -341,6 +355,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     a.w_half_stride = P.c1.tc.half_stride[vb][vk];
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
+    a.dbg = env_int("HFG_TC_DBG", 0);
     a.b1 = P.c1.bias; a.b2 = P.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
@@ -374,6 +389,9 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
     const double bytes = (double)B * T * C * ESZ * (out ? 2 : 1) +
                          (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
+    if (env_int("HFG_TC_VERBOSE", 0))
+        fprintf(stderr, "[pair] N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d\n",
+                a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles);
     h->prof_begin(st, label, flops, bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
