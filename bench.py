@@ -87,7 +87,7 @@ class ClockSampler:
     def stop(self, t_begin=None, t_end=None):
         """Summarise the samples taken inside [t_begin, t_end] (the timed region).  A region shorter
         than nvidia-smi's sampling period may hold none: then every sample taken while the bench was
-        under load (warm-up .. end of the e2e loop) is used and the window is named in the result."""
+        under load (warm-up .. end of the timed region) is used and the window is named in the result."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -98,7 +98,7 @@ class ClockSampler:
         window = "timed region"
         picked = [l for (t, l) in self.lines if t_begin is None or (t_begin <= t <= t_end)]
         if not picked:
-            window = "bench under load (warm-up .. e2e loop); timed region shorter than the sampling period"
+            window = "bench under load (warm-up .. timed region); timed region shorter than the sampling period"
             picked = [l for (_, l) in self.lines]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -211,7 +211,7 @@ def main():
     gen = pkg.HiFiGANGenerator(**cfg, mode=args.mode).to(dev)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_weights(cfg, 0).items()})
     # every rank gets its own utterances (seed by rank): utterance sharding
-    mel_host = torch.from_numpy(synth.make_mel(1 + rank, B, cfg["n_mels"], T))
+    mel_host = torch.from_numpy(synth.make_mel(1 + rank, B, cfg["n_mels"], T)).pin_memory()   # page-locked input
     mel = mel_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -237,6 +237,10 @@ def main():
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
 
         # ---------------- end-to-end region (host buffers) ----------------
+        # nvidia-smi polling takes driver locks that stall the synchronous host calls of this loop by
+        # more than a millisecond per step (tools/e2e_breakdown.py vs this loop with the sampler on),
+        # so the sampler covers warm-up + the device-timed region and is stopped here.
+        clocks = sampler.stop(t_begin, t_end)
         e2e_steps = args.e2e_steps or steps
         for _ in range(2):
             gen(mel_host)
@@ -246,7 +250,6 @@ def main():
             wav_host = gen(mel_host)                 # synchronous: returns a host tensor
         e2e_s = time.perf_counter() - t0
         barrier()
-        clocks = sampler.stop(t_begin, t_end)
 
         # ---------------- other arithmetic modes + output quality (untimed for `value`) ----------------
         # the same batch in the strict fp32 mode is the on-device stand-in for the reference output

@@ -32,6 +32,7 @@ namespace hfg {
 
 constexpr int kPairEpiWarps = 8;
 constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+constexpr int kPairMaxSA = 6;                     // activation ring slots (K blocks, possibly of several tiles ahead)
 
 struct TcPairArgs {
     const uint8_t* a; long long a_bstride, a_pstride;     // leaky_relu(x) planes
@@ -101,12 +102,12 @@ tc_pair_kernel(const TcPairArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + N);
     const uint32_t bar0 = smem_u32(bars);
     auto A_FULL = [&](int i) { return bar0 + 8u * i; };
-    auto A_EMPTY = [&](int i) { return bar0 + 8u * (kMaxSA + i); };
-    auto W_FULL = [&](int i) { return bar0 + 8u * (2 * kMaxSA + i); };
-    auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kMaxSA + kMaxSW + i); };
-    const uint32_t ACC1_FULL = bar0 + 8u * (2 * kMaxSA + 2 * kMaxSW);
+    auto A_EMPTY = [&](int i) { return bar0 + 8u * (kPairMaxSA + i); };
+    auto W_FULL = [&](int i) { return bar0 + 8u * (2 * kPairMaxSA + i); };
+    auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kPairMaxSA + kMaxSW + i); };
+    const uint32_t ACC1_FULL = bar0 + 8u * (2 * kPairMaxSA + 2 * kMaxSW);
     const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 3 + kMaxSA + kMaxSW);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairMaxSA + 2 * kMaxSW + 3);
 
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * N) ncols <<= 1;

@@ -265,10 +265,11 @@ struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ
 
 static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
     // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
-    // (profiles/r1_tuning.md): C = 64..128 with k >= 5 in bf16, C = 64..128 for every k in tf32.  C = 256
-    // (TMEM-limited to one 128-row sub-tile per CTA) and C = 32 stay single-CTA.
+    // (profiles/r1_tuning.md sections 5 and 7): every C >= 64 layer, except tf32 C = 256 whose fp32 H tile
+    // leaves too little shared memory (the fused pair measured slower than two unfused launches there).
+    // C = 32 stays single-CTA (0.560 vs 0.582 ms for the stage).
     const int N = P.c1.cout;
-    const int dflt = (N >= 64 && N <= 128 && (P.c1.k >= 5 || !bf16)) ? 2 : 1;
+    const int dflt = (N >= 64 && (bf16 || N <= 128)) ? 2 : 1;
     const int want = env_int("HFG_TC_PAIR_CTAS", dflt);
     return (want == 2 && P.c1.tc.w_pair[bf16 ? 1 : 0][1][0] && P.c2.tc.w_pair[bf16 ? 1 : 0][1][0]) ? 2 : 1;
 }
@@ -299,11 +300,13 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         // bound by the MMA warp's per-stage round trip (two mbarrier waits, fence, commit), so stages are made
         // as FAT as shared memory allows -- G taps per stage with at least `sw_min` stages -- rather than deep.
         // When a second CTA can share the SM the budget is half the SM (that co-residency is worth more).
-        const int sa = std::min(kMaxSA, n_kb);
+        // A ring: `sa_tiles` tiles of activations in flight (the next tile's rows stream in while this
+        // tile is in its conv2 / epilogues)
         const int R1 = MT * 128 + 2 * p1;
         const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
         const size_t tap_bytes = (size_t)NB * nck_max * 16;
-        const size_t fixed = (size_t)sa * R1 * nck_max * 16 + (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + 384;
+        const size_t a_stage = (size_t)R1 * nck_max * 16;
+        const size_t fixed0 = (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + (size_t)env_int("HFG_TC_PAIR_PAD", 512);
         int ncols = 32;
         while (ncols < 2 * MT * N) ncols <<= 1;
         const int sw_min = std::max(2, env_int("HFG_TC_PAIR_SWMIN", 2));
@@ -311,6 +314,19 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         auto make = [&](size_t budget) {
             PairGeom c{};
             c.ok = false;
+            // A ring.  One slot per K block of the tile (the whole tile resident: conv1 never waits for a slot
+            // to drain) where that still leaves W stages of >= 3 taps, else two slots: tf32 C=128 gains 9 %
+            // with 4 slots (G = 4), bf16 C=256 loses 7 % (G = 2 instead of 3) -- profiles/r1_tuning.md section 7.
+            // More than one tile in flight (HFG_TC_PAIR_SA_TILES) measured slower everywhere.
+            int sa = std::min(kPairMaxSA, n_kb * std::max(1, env_int("HFG_TC_PAIR_SA_TILES", 1)));
+            sa = std::min(sa, std::max(1, env_int("HFG_TC_PAIR_SA_CAP", kPairMaxSA)));
+            const int sa_floor = std::min(2, n_kb);
+            auto taps_per_stage = [&](int s_a) -> long long {
+                const long long room = (long long)budget - (long long)fixed0 - (long long)s_a * (long long)a_stage;
+                return room <= 0 ? 0 : room / (long long)(sw_min * tap_bytes);
+            };
+            while (sa > sa_floor && taps_per_stage(sa) < std::min(k, 3)) --sa;
+            const size_t fixed = fixed0 + sa * a_stage;
             if (fixed + sw_min * tap_bytes > budget) return c;
             int G = (int)std::min<size_t>((size_t)k, (budget - fixed) / (sw_min * tap_bytes));
             G = (int)std::min<size_t>((size_t)G, std::max<size_t>(1, stage_cap / tap_bytes));
@@ -325,6 +341,9 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         };
         PairGeom c = make((size_t)kTcSmemLimit);
         if (!c.ok) continue;
+        // a larger tile is not worth W stages thinner than 3 taps (tf32 C=128: MT=2 with G=1 1.63 ms for the
+        // stage, MT=1 with G=4 1.43 ms)
+        if (c.G < std::min(k, 3) && MT > 1) continue;
         // a second CTA could share the SM: worth more than fat stages for N <= 64 (stage 2: 63.6 vs 69.5 us,
         // stage 3: 73.8 vs 124 us at k = 11), not for N = 128 (115.8 vs 98.6 us)
         if (512 / ncols >= 2 && env_int("HFG_TC_PAIR_OCC2", N <= 64 ? 1 : 0)) {
