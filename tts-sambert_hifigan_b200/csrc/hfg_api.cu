@@ -414,6 +414,7 @@ void hfg_destroy(hfg_handle* h) {
     if (!h) return;
     h->free_device_weights();
     h->free_host_path();
+    h->free_streams();
     delete h;
 }
 

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -73,6 +75,7 @@ struct hfg_handle {
     std::string last_error;
     int64_t launches = 0;
     int mel_layout = 0;       // 0 = [B, n_mels, T] (reference), 1 = [B, T, n_mels] (acoustic-model output)
+    unsigned long long* pair_timeline = nullptr;   // tuning only: phase stamps of the fused pair kernel (hfg_bench_layer)
 
     std::map<std::string, hfg::HostTensor> sd;   // raw state_dict as set by the caller
 
@@ -111,6 +114,36 @@ struct hfg_handle {
     void prof_end(cudaStream_t st) {
         if (!profiling) return;
         hfg::check_cuda(cudaEventRecord(prof.back().e1, st), "cudaEventRecord");
+    }
+
+    // Side streams of the tensor-core path: the resblocks of one MRF are independent until their last pair
+    // (reference models/hifigan.py:126-131), so resblock j runs on stream j % kStreams; fork / join and the
+    // order of the running-sum updates are expressed with events (no host synchronisation).
+    static constexpr int kStreams = 3;
+    cudaStream_t side[kStreams - 1] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kStreams - 1] = {nullptr, nullptr}, ev_sum[HFG_MAX_STAGES] = {};
+    void ensure_streams() {
+        if (ev_fork) return;
+        using hfg::check_cuda;
+        // side streams outrank the caller's stream: they carry the longer resblocks (the critical path), whose
+        // CTAs should be placed first whenever SMs free up
+        int prio_least = 0, prio_greatest = 0;
+        check_cuda(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest), "cudaDeviceGetStreamPriorityRange");
+        for (int i = 0; i < kStreams - 1; ++i)
+            check_cuda(cudaStreamCreateWithPriority(&side[i], cudaStreamNonBlocking,
+                                                    getenv("HFG_TC_STREAM_NOPRIO") ? prio_least
+                                                        : std::max(prio_greatest, prio_least - 1 - i)),
+                       "cudaStreamCreateWithPriority");
+        check_cuda(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
+        for (auto& e : ev_join) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+        for (auto& e : ev_sum) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    }
+    void free_streams() {
+        for (auto& s : side) { if (s) cudaStreamDestroy(s); s = nullptr; }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        ev_fork = nullptr;
+        for (auto& e : ev_join) { if (e) cudaEventDestroy(e); e = nullptr; }
+        for (auto& e : ev_sum) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
 
     // hfg_forward_host resources

@@ -601,7 +601,7 @@ __global__ void tc_unpack_stage(const uint8_t* __restrict__ in, float* __restric
         y[((size_t)b * C + chunk * CW + i) * T + t] = lrelu_inv(v[i], inv_slope);
 }
 
-// Zero the padding rows [0, PADL) and [PADL + T, TP) of every plane of up to 40 buffers.
+// Zero the padding rows [0, PADL) and [PADL + T, TP) of every plane of up to 40 buffers per launch.
 struct PadJob { uint8_t* base; long long planes; int TP; int T; };
 struct PadJobs { PadJob job[40]; int n; };
 __global__ void tc_zero_pads(const PadJobs jobs) {

@@ -54,10 +54,18 @@ struct TcPairArgs {
     int tap_group;    // taps per W stage
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
-    int dbg;          // timing experiments only (results are wrong): 1 = no weight copies, 2 = no activation copies
+    int dbg;          // timing experiments only (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
     int tiles_per_batch, n_tiles;
     float slope;
+    unsigned long long* timeline;   // tuning only (tools/pair_timeline.py): clock64 stamps, [cta < 4][tile < 16][event < 16]
 };
+
+// per-tile phase stamps of the first CTAs (null pointer in production: one predicated-off store per event)
+#define HFG_TL(ev, tile_ord)                                                                                  \
+    do {                                                                                                      \
+        if (a.timeline && blockIdx.x < 4 && (tile_ord) < 16 && lane == 0)                                     \
+            a.timeline[((size_t)blockIdx.x * 16 + (tile_ord)) * 16 + (ev)] = (unsigned long long)clock64();   \
+    } while (0)
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -174,6 +182,7 @@ tc_pair_kernel(const TcPairArgs a) {
             bool did = false;
             if (a_t < n_my && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
+                if (a_kb == 0) HFG_TL(0, a_t);
                 if (leader && (a.dbg & 2)) mbar_arrive(A_FULL(sa_i));
                 if (leader && !(a.dbg & 2)) {
                     const uint8_t* ab = tile_src(tile_of(sched0 + a_t * sched_step));
@@ -192,6 +201,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks - KBC * w_kb) < KBC ? (n_chunks - KBC * w_kb) : KBC;
                 const int tap0 = w_g * G;
                 const int g = (k - tap0) < G ? (k - tap0) : G;
+                if (w_conv == 0 && w_kb == 0 && w_g == 0) HFG_TL(11, w_t);
                 if (leader && (a.dbg & 1)) mbar_arrive(W_FULL(sw_i));
                 if (leader && !(a.dbg & 1)) {
                     const uint8_t* w = w_conv ? a.w2 : a.w1;
@@ -254,6 +264,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int ksteps = nck >> 1;
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 tc_fence_after();
+                if (kb == 0) HFG_TL(1, it);
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
                     const int g = (k - tap0) < G ? (k - tap0) : G;
@@ -261,9 +272,9 @@ tc_pair_kernel(const TcPairArgs a) {
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int tt = 0; tt < g; ++tt) {
+                        for (int tt = 0; tt < g && !(a.dbg & 16); ++tt) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
-                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil);
+                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * ((a.dbg & 4) ? 8 : a.dil));
                             for (int mt = 0; mt < MT; ++mt)
                                 umma_ksteps<BF16, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
                                                         2u * (uint32_t)R1, 2u * (uint32_t)NB, idesc, ksteps,
@@ -281,9 +292,11 @@ tc_pair_kernel(const TcPairArgs a) {
             }
             if (leader) commit(ACC1_FULL);
             __syncwarp();
+            HFG_TL(2, it);
             // ---- conv2: acc2 (pre-loaded with x + b2) += sum_{kb,tap} H(+tap rows) * W2 ----
             if constexpr (CTAS == 2) mbar_wait_cluster(H_READY, it & 1); else mbar_wait(H_READY, it & 1);
             tc_fence_after();
+            HFG_TL(3, it);
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
@@ -294,9 +307,9 @@ tc_pair_kernel(const TcPairArgs a) {
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int tt = 0; tt < g; ++tt) {
+                        for (int tt = 0; tt < g && !(a.dbg & 16); ++tt) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
-                            const uint32_t h_lo1 = h_lo0 + (uint32_t)(tap0 + tt);
+                            const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * ((a.dbg & 4) ? 8 : 1));
                             for (int mt = 0; mt < MT; ++mt)
                                 umma_ksteps<BF16, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
                                                         2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc, ksteps, 1u);
@@ -309,6 +322,7 @@ tc_pair_kernel(const TcPairArgs a) {
             }
             if (leader) commit(ACC2_FULL);
             __syncwarp();
+            HFG_TL(4, it);
         }
         }   // leader / single-CTA issue path
     } else {
@@ -336,8 +350,9 @@ tc_pair_kernel(const TcPairArgs a) {
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 mbar_wait(A_FULL(sa_i), sa_ph);
+                if (kb == 0 && e == 0) HFG_TL(5, it);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
-                for (int mt = mt_first; mt < MT; mt += mt_step) {
+                for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
                     const int lr = mt * 128 + row;                      // output row inside the tile
                     const int t = t0 + lr;
                     const bool add_prev = add_prev_mode && real && lr < a.TO && t < a.T;
@@ -367,9 +382,11 @@ tc_pair_kernel(const TcPairArgs a) {
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
             }
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
+            if (e == 0) HFG_TL(6, it);
             mbar_wait(ACC1_FULL, it & 1);
             tc_fence_after();
-            for (int mt = mt_first; mt < MT; mt += mt_step) {
+            if (e == 0) HFG_TL(7, it);
+            for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
                 const float keep = (th >= 0 && th < a.T) ? 1.f : 0.f;   // conv2 zero-pads ITS input
@@ -406,9 +423,11 @@ tc_pair_kernel(const TcPairArgs a) {
                 else mbar_arrive(H_READY);
             }
             // ---------- epi2: acc2 -> global ----------
+            if (e == 0) HFG_TL(8, it);
             mbar_wait(ACC2_FULL, it & 1);
             tc_fence_after();
-            for (int mt = mt_first; mt < MT; mt += mt_step) {
+            if (e == 0) HFG_TL(9, it);
+            for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
                 const int lr = mt * 128 + row;
                 const int t = t0 + lr;
                 const bool valid = real && lr < a.TO && t < a.T;
@@ -445,6 +464,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 }
             }
             tc_fence_before();           // order these TMEM reads before the next tile's tcgen05.st / MMA
+            if (e == 0) HFG_TL(10, it);
         }
     }
     tc_fence_before();

@@ -179,7 +179,9 @@ static inline TcPlane tc_plane(int B, int C, long long T, int cw, size_t& cursor
 
 struct TcPlan {
     TcPlane mel, pre;                       // packed mel, conv_pre output
-    struct Stage { TcPlane X, H, R, Y, ACC; } st[HFG_MAX_STAGES];
+    // per stage: X = upsampler output, Y = MRF output, ACC = fp32 running sum over the resblocks, and per
+    // resblock (they run concurrently) two ping-pong planes R, H plus a scratch S for the unfused fallback
+    struct Stage { TcPlane X, Y, ACC; struct { TcPlane R, H, S; } rb[HFG_MAX_STAGES]; } st[HFG_MAX_STAGES];
     size_t total = 0;
 };
 
@@ -194,9 +196,12 @@ static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
         const UpLayer& U = h->ups[i];
         t = (t - 1) * U.u - 2 * U.p + U.k;
         p.st[i].X = tc_plane(B, U.cout, t, cw, cur);
-        p.st[i].H = tc_plane(B, U.cout, t, cw, cur);
-        p.st[i].R = tc_plane(B, U.cout, t, cw, cur);
         p.st[i].Y = tc_plane(B, U.cout, t, cw, cur);
+        for (int j = 0; j < h->cfg.num_resblocks; ++j) {
+            p.st[i].rb[j].R = tc_plane(B, U.cout, t, cw, cur);
+            p.st[i].rb[j].H = tc_plane(B, U.cout, t, cw, cur);
+            p.st[i].rb[j].S = tc_plane(B, U.cout, t, cw, cur);
+        }
         p.st[i].ACC = tc_plane(B, U.cout, t, 4, cur);          // fp32 accumulator cells
     }
     p.total = cur;
@@ -384,6 +389,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     a.tiles_per_batch = (T + g.TO - 1) / g.TO;
     a.n_tiles = a.tiles_per_batch * B;
     a.slope = 0.1f;
+    a.timeline = h->pair_timeline;
     // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
     const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
@@ -440,17 +446,31 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     // ---- zero the padding rows of every plane (one launch) ----
     {
         PadJobs jobs{};
+        auto flush = [&]() {
+            if (!jobs.n) return;
+            h->prof_begin(st, "zero_pads", 0, 0);
+            tc_zero_pads<<<dim3(64, jobs.n), 256, 0, st>>>(jobs);
+            h->prof_end(st);
+            check_cuda(cudaGetLastError(), "tc_zero_pads launch");
+            jobs.n = 0;
+        };
         auto add = [&](const TcPlane& p) {
             jobs.job[jobs.n++] = PadJob{ptr(p), (long long)B * p.nchunks, p.TP, p.T};
+            if (jobs.n == 40) flush();
         };
+        // which planes are ever read: R/H only with more than one pair per resblock, S only without the fused kernel
         add(plan.mel); add(plan.pre);
         for (size_t i = 0; i < h->ups.size(); ++i) {
-            add(plan.st[i].X); add(plan.st[i].H); add(plan.st[i].R); add(plan.st[i].Y);
+            add(plan.st[i].X); add(plan.st[i].Y);
+            for (int j = 0; j < n_rb; ++j) {
+                bool fused = true;
+                for (auto& P : h->mrfs[i][j]) fused = fused && tc_pair_geometry(h, P, plan.st[i].X.nchunks, BF16).ok;
+                if (h->mrfs[i][j].size() > 1) add(plan.st[i].rb[j].R);
+                if (h->mrfs[i][j].size() > 2) add(plan.st[i].rb[j].H);
+                if (!fused) add(plan.st[i].rb[j].S);
+            }
         }
-        h->prof_begin(st, "zero_pads", 0, 0);
-        tc_zero_pads<<<dim3(64, jobs.n), 256, 0, st>>>(jobs);
-        h->prof_end(st);
-        check_cuda(cudaGetLastError(), "tc_zero_pads launch");
+        flush();
     }
     // ---- mel -> chunk planes ----
     {
@@ -467,7 +487,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         tc_unpack_stage<BF16><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
         check_cuda(cudaGetLastError(), "tc_unpack_stage launch");
     };
-    auto conv = [&](const ConvLayer& L, const TcPlane& in, const TcPlane* out, const TcPlane* res,
+    auto conv = [&](cudaStream_t st, const ConvLayer& L, const TcPlane& in, const TcPlane* out, const TcPlane* res,
                     const TcPlane* acc, int acc_mode, const char* label) {
         TcConvArgs a{};
         a.a = ptr(in); a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
@@ -495,7 +515,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     };
 
     // conv_pre (reference :238); its output is stored as leaky_relu(x) for ups[0] (:244)
-    conv(h->pre, plan.mel, &plan.pre, nullptr, nullptr, TC_ACC_NONE, "conv_pre");
+    conv(st, h->pre, plan.mel, &plan.pre, nullptr, nullptr, TC_ACC_NONE, "conv_pre");
     dump(0, plan.pre);
 
     const TcPlane* cur = &plan.pre;
@@ -525,33 +545,75 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         }
         dump(1 + 2 * (int)i, S.X);
 
-        // MRF (reference :116-131)
-        for (int j = 0; j < n_rb; ++j) {
-            const auto& rb = h->mrfs[i][j];
-            const std::string lab = "mrf" + std::to_string(i) + ".k" + std::to_string(rb[0].c1.k);
-            const TcPlane* r = &S.X;
-            for (size_t l = 0; l < rb.size(); ++l) {
-                const bool last = (l + 1 == rb.size());
-                int mode = TC_ACC_NONE;
-                if (last && n_rb > 1) mode = j == 0 ? TC_ACC_WRITE : (j == n_rb - 1 ? TC_ACC_FINAL : TC_ACC_ADD);
-                // destination of this pair: ping-pong between R and H; the last pair feeds the MRF sum / Y
-                const TcPlane* dst = last ? ((mode == TC_ACC_WRITE || mode == TC_ACC_ADD) ? nullptr : &S.Y)
-                                          : (r == &S.R ? &S.H : &S.R);
-                const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, BF16);
-                if (g.ok) {
-                    tc_launch_pair<BF16>(h, st, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
-                                         dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
-                                         mode != TC_ACC_NONE ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
-                                         S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb, B, S.X.T, lab.c_str());
-                } else {
-                    // unfused fallback: conv1 -> T (scratch), conv2 (+ residual) -> dst
-                    const TcPlane* scratch = nullptr;
-                    for (const TcPlane* c : {&S.H, &S.R, &S.Y})
-                        if (c != r && c != dst) { scratch = c; break; }
-                    conv(rb[l].c1, *r, scratch, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
-                    conv(rb[l].c2, *scratch, dst, r, mode != TC_ACC_NONE ? &S.ACC : nullptr, mode, lab.c_str());
+        // MRF (reference :116-131).  The resblocks only meet in the running sum, so resblock j is enqueued on
+        // stream j % n_streams: the tail of one kernel (persistent grids rarely divide evenly: 96 tile pairs
+        // on 74 clusters in stage 0) is filled by the next resblock's CTAs.  Per-launch profiling serialises
+        // everything on `st` so that each kernel is timed alone.
+        const int n_streams = (h->profiling || n_rb < 2) ? 1 : std::max(1, std::min({env_int("HFG_TC_STREAMS", 3),
+                                                                                      (int)hfg_handle::kStreams, n_rb}));
+        // Stream assignment, measured at the bench workload (profiles/r1_tuning.md section 8; ms/step bf16 / tf32):
+        // one stream 2.49 / 4.38; three streams, resblocks in natural order with the SHORT ones (k = 3, 7) on
+        // the higher-priority side streams and the longest on the caller's stream 2.25 / 4.10; longest first
+        // on the highest priority (HFG_TC_STREAM_LPT=1) 2.35 / 4.13; no priorities 2.29 / 4.16; two streams
+        // 2.38 / 4.19.  The short resblocks finish their running-sum updates early and their epilogue-bound
+        // kernels fill the gaps of the MMA-bound long ones.
+        std::vector<int> order(n_rb), slot(n_rb, 0);
+        for (int j = 0; j < n_rb; ++j) order[j] = j;
+        auto cost = [&](int j) { int c = 0; for (auto& P : h->mrfs[i][j]) c += P.c1.k + P.c2.k; return c; };
+        if (n_streams > 1 && env_int("HFG_TC_STREAM_LPT", 0))
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
+        for (int r = 0; r < n_rb; ++r) slot[order[r]] = (n_streams - 1 - (r % n_streams));   // rank 0 -> last side stream
+        auto stream_of = [&](int j) { return slot[j] == 0 ? st : h->side[slot[j] - 1]; };
+        if (n_streams > 1) {
+            h->ensure_streams();
+            check_cuda(cudaEventRecord(h->ev_fork, st), "cudaEventRecord(fork)");
+            for (int s = 1; s < n_streams; ++s)
+                check_cuda(cudaStreamWaitEvent(h->side[s - 1], h->ev_fork, 0), "cudaStreamWaitEvent(fork)");
+        }
+        // pass 0: every pair but the last, costliest resblock first; pass 1: the last pairs in resblock order,
+        // because the running sum is updated in that order (WRITE, ADD ..., FINAL) and an event has to be
+        // recorded before the wait on it is enqueued
+        std::vector<const TcPlane*> src(n_rb, &S.X);
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int q = 0; q < n_rb; ++q) {
+                const int j = pass == 0 ? order[q] : q;
+                const auto& rb = h->mrfs[i][j];
+                const auto& W = S.rb[j];
+                cudaStream_t sj = stream_of(j);
+                const std::string lab = "mrf" + std::to_string(i) + ".k" + std::to_string(rb[0].c1.k);
+                const size_t l_begin = pass == 0 ? 0 : rb.size() - 1, l_end = pass == 0 ? rb.size() - 1 : rb.size();
+                for (size_t l = l_begin; l < l_end; ++l) {
+                    const TcPlane* r = src[j];
+                    const bool last = (l + 1 == rb.size());
+                    int mode = TC_ACC_NONE;
+                    if (last && n_rb > 1) mode = j == 0 ? TC_ACC_WRITE : (j == n_rb - 1 ? TC_ACC_FINAL : TC_ACC_ADD);
+                    if (last && j > 0 && n_streams > 1 && stream_of(j - 1) != sj)
+                        check_cuda(cudaStreamWaitEvent(sj, h->ev_sum[j - 1], 0), "cudaStreamWaitEvent(sum)");
+                    // destination of this pair: ping-pong between R and H; the last pair feeds the MRF sum / Y
+                    const TcPlane* dst = last ? ((mode == TC_ACC_WRITE || mode == TC_ACC_ADD) ? nullptr : &S.Y)
+                                              : (r == &W.R ? &W.H : &W.R);
+                    const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, BF16);
+                    if (g.ok) {
+                        tc_launch_pair<BF16>(h, sj, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
+                                             dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
+                                             mode != TC_ACC_NONE ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
+                                             S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb, B, S.X.T, lab.c_str());
+                    } else {
+                        // unfused fallback: conv1 -> scratch, conv2 (+ residual) -> dst
+                        conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
+                        conv(sj, rb[l].c2, W.S, dst, r, mode != TC_ACC_NONE ? &S.ACC : nullptr, mode, lab.c_str());
+                    }
+                    if (last && n_streams > 1 && j + 1 < n_rb)
+                        check_cuda(cudaEventRecord(h->ev_sum[j], sj), "cudaEventRecord(sum)");
+                    if (!last) src[j] = dst;
                 }
-                if (!last) r = dst;
+            }
+        }
+        if (n_streams > 1) {
+            // join: everything enqueued on the side streams precedes what follows on `st`
+            for (int s = 1; s < n_streams; ++s) {
+                check_cuda(cudaEventRecord(h->ev_join[s - 1], h->side[s - 1]), "cudaEventRecord(join)");
+                check_cuda(cudaStreamWaitEvent(st, h->ev_join[s - 1], 0), "cudaStreamWaitEvent(join)");
             }
         }
         cur = &S.Y;
@@ -611,6 +673,28 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
             tc_launch_conv<BF16>(h, st, a, B, L.cout, "bench", 0, 0);
     };
     for (int i = 0; i < 3; ++i) launch();
+    if (const char* tl_path = getenv("HFG_TC_TIMELINE")) {
+        // tuning only: one extra launch with per-phase clock stamps of the first 4 CTAs, dumped as text
+        const size_t n = 4 * 16 * 16;
+        unsigned long long* d = nullptr;
+        check_cuda(cudaMalloc((void**)&d, n * 8), "cudaMalloc(timeline)");
+        check_cuda(cudaMemset(d, 0, n * 8), "cudaMemset(timeline)");
+        h->pair_timeline = d;
+        launch();
+        h->pair_timeline = nullptr;
+        std::vector<unsigned long long> hbuf(n);
+        check_cuda(cudaMemcpy(hbuf.data(), d, n * 8, cudaMemcpyDeviceToHost), "cudaMemcpy(timeline)");
+        cudaFree(d);
+        if (FILE* f = fopen(tl_path, "a")) {
+            fprintf(f, "# stage=%d resblock=%d pair=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d ctas=%d\n", stage, resblock, pair,
+                    L.cout, L.k, P.c1.dil, g.MT, g.G, g.sa, g.sw, g.ctas);
+            for (size_t i = 0; i < n; i += 16) {
+                for (int e = 0; e < 16; ++e) fprintf(f, "%llu ", hbuf[i + e]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     check_cuda(cudaEventRecord(e0, st), "record");
     for (int i = 0; i < iters; ++i) launch();
     check_cuda(cudaEventRecord(e1, st), "record");
