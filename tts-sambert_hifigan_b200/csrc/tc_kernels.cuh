@@ -478,6 +478,7 @@ tc_conv_kernel(const TcConvArgs a) {
         const int half = (warp - 2) >> 2;                   // the two warps of a quarter alternate 32-column steps
         const int qlane = quarter * 32 + lane;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        const float inv_div = 1.0f / a.div;
         const bool add_prev = a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL;
         const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         for (int mt = 0; mt < MT; ++mt) {
@@ -531,7 +532,7 @@ tc_conv_kernel(const TcConvArgs a) {
                     }
                     if (a.acc_mode == TC_ACC_FINAL) {        // / len(resblocks)  (reference :131)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
+                        for (int i = 0; i < 16; ++i) v[i] *= inv_div;
                     }
                     if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll

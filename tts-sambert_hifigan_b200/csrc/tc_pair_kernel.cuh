@@ -336,6 +336,7 @@ tc_pair_kernel(const TcPairArgs a) {
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        const float inv_div = 1.0f / a.div;           // MRF mean as a multiplication (tensor-core modes are not bit-exact anyway)
         const long long a_plane = (long long)R1 * 16, h_plane = (long long)RH * 16;
         const bool add_prev_mode = (a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL);
         const bool acc_store_mode = (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD);
@@ -386,10 +387,12 @@ tc_pair_kernel(const TcPairArgs a) {
             mbar_wait(ACC1_FULL, it & 1);
             tc_fence_after();
             if (e == 0) HFG_TL(7, it);
+            // only tiles that touch an utterance edge have H rows outside [0, T) to zero
+            const bool edge_tile = (t0 - a.p2 < 0) || (t0 - a.p2 + MT * 128 > a.T);
             for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
-                const float keep = (th >= 0 && th < a.T) ? 1.f : 0.f;   // conv2 zero-pads ITS input
+                const bool drop = edge_tile && !(th >= 0 && th < a.T);  // conv2 zero-pads ITS input
                 uint8_t* hp = sH + (size_t)hr * 16;
                 const uint32_t tbase = acc1 + lane_sel + (uint32_t)(mt * N);
                 for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
@@ -403,14 +406,14 @@ tc_pair_kernel(const TcPairArgs a) {
                     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r0[i]);
                     add_bias16(v, sB1 + c0);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope) * keep;
+                    for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
                     store_cells16<BF16>(hp + (long long)(c0 / CW) * h_plane, h_plane, v);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
                         add_bias16(v, sB1 + c0 + 16);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope) * keep;
+                        for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
                         store_cells16<BF16>(hp + (long long)((c0 + 16) / CW) * h_plane, h_plane, v);
                     }
                 }
@@ -454,7 +457,7 @@ tc_pair_kernel(const TcPairArgs a) {
                         } else {
                             if (a.acc_mode == TC_ACC_FINAL) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i) v[i] = v[i] / a.div;
+                                for (int i = 0; i < 16; ++i) v[i] *= inv_div;
                             }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
