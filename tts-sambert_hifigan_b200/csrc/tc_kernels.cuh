@@ -357,11 +357,13 @@ tc_conv_kernel(const TcConvArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSA + 2 * kMaxSW + 1);
 
     // tile coordinates
-    const int b = blockIdx.x / a.tiles_per_batch;
-    const int q0 = (blockIdx.x % a.tiles_per_batch) * MT * 128;
-    const int n_tiles = gridDim.y / a.phases;
-    const int phase = blockIdx.y / n_tiles;
-    const int ntile = blockIdx.y % n_tiles;
+    // grid.x = (phase, channel tile) runs fastest: the CTAs that share an activation tile (and, for the
+    // polyphase upsamplers, interleave their 16-byte cells in the same output sectors) are co-scheduled
+    const int b = blockIdx.y / a.tiles_per_batch;
+    const int q0 = (blockIdx.y % a.tiles_per_batch) * MT * 128;
+    const int n_tiles = gridDim.x / a.phases;
+    const int phase = blockIdx.x / n_tiles;
+    const int ntile = blockIdx.x % n_tiles;
     int taps = a.taps_max;
     if (a.phases > 1) taps = (a.k - phase + a.u - 1) / a.u;
     const int n_chunks = a.a_nchunks;

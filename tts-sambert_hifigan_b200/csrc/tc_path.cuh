@@ -255,7 +255,7 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     a.R = MT * 128 + span;
     a.tiles_per_batch = (a.n_q + MT * 128 - 1) / (MT * 128);
     const size_t smem = smem_need(MT, sa, sw);
-    dim3 grid(B * a.tiles_per_batch, a.phases * (cout / a.N), 1);
+    dim3 grid(a.phases * (cout / a.N), B * a.tiles_per_batch, 1);
     h->prof_begin(st, label, flops, bytes);
     // 8 epilogue warps when the CTA owns its SM anyway (big tiles: latency-bound epilogue, profiles/r1_tuning.md);
     // 4 when two CTAs can share the SM (narrow layers), which hides the epilogue better than more warps
