@@ -604,12 +604,17 @@ __global__ void tc_unpack_stage(const uint8_t* __restrict__ in, float* __restric
         y[((size_t)b * C + chunk * CW + i) * T + t] = lrelu_inv(v[i], inv_slope);
 }
 
-// Zero the padding rows [0, PADL) and [PADL + T, TP) of every plane of up to 40 buffers per launch.
+// Zero the padding rows a VALID output can depend on: the kPadL rows in front of the data and the first
+// kZeroTail rows after it (receptive halo of any layer <= 32 rows; polyphase / conv_post overhang <= 4).
+// Rows further out are only ever read into accumulator rows that are never stored (a UMMA output row
+// depends on its own operand rows only), so they may hold anything.  Up to 40 buffers per launch.
+constexpr int kZeroTail = 96;
 struct PadJob { uint8_t* base; long long planes; int TP; int T; };
 struct PadJobs { PadJob job[40]; int n; };
 __global__ void tc_zero_pads(const PadJobs jobs) {
     const PadJob j = jobs.job[blockIdx.y];
-    const int pad_rows = j.TP - j.T;                       // front PADL rows + tail rows
+    const int tail = (j.TP - kPadL - j.T) < kZeroTail ? (j.TP - kPadL - j.T) : kZeroTail;
+    const int pad_rows = kPadL + tail;                     // front rows + tail rows
     const long long total = j.planes * pad_rows;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
