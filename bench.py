@@ -346,6 +346,7 @@ def main():
             "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
             "peak_source": peaks["source"] + "; " + peak_note,
             "share_of_step": dom["ms"] / step_ms_prof if step_ms_prof else None,
+            "serial_step_ms": step_ms_prof,
             "all_mrf_launches": {"launches": sum(p["launches"] for p in mrf), "tflops": mrf_tflops,
                                  "frac": mrf_tflops / tensor_peak, "share_of_step": mrf_ms / step_ms_prof},
             "per_stage": [{"kernel": p["kernel"], "launches": p["launches"], "ms": round(p["ms"], 4),
@@ -362,6 +363,8 @@ def main():
                                    f"({audio_seconds(1, T):.2f} s utterances) per GPU, mode {args.mode}",
                        "parallelism": f"utterance-sharded x{world}, no data-path collective",
                        "l2": "256 MiB flush between timed steps",
+                       "streams": "timed steps: the 3 resblocks of each MRF on 3 streams (fork/join events); the "
+                                  "per-kernel roofline pass serialises them so every launch is timed alone",
                        "e2e_timer": "host perf_counter around synchronous calls"},
             "tflops_per_gpu": flops_step * steps / (dev_ms_max / 1e3) / 1e12,
             "e2e": {"value": e2e_val, "unit": UNIT,
