@@ -15,8 +15,8 @@ data-path collective): "scaling": "weak".
          mel already resident in HBM), whole-job: sum of audio-seconds over ranks
          / max over ranks of the timed duration.
   e2e    the same metric through the public call a user makes --
-         HiFiGANGenerator(mel_cpu) -> hfg_forward_host: pageable host mel ->
-         pinned -> H2D -> kernels -> D2H -> host wav, every step.
+         HiFiGANGenerator(mel_cpu) -> hfg_forward_host_ex: page-locked host mel ->
+         H2D -> kernels -> D2H into a page-locked host wav, every step.
   roofline      dominant kernel class (the MRF convolutions), from per-launch
                 CUDA events inside the library (hfg_set_profiling).
   cpu_baseline  the oracle's ATen restatement of the reference (oracle/torch_port.py;
@@ -169,8 +169,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("HFG_BENCH_MODE", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--batch", type=int, default=WORKLOAD["batch"])
@@ -234,7 +234,8 @@ def main():
             ev[s][1].record()
         torch.cuda.synchronize(); barrier()
         t_end = time.time()
-        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        step_ms = sorted(a.elapsed_time(b) for a, b in ev)
+        dev_ms = sum(step_ms)
 
         # ---------------- end-to-end region (host buffers) ----------------
         # nvidia-smi polling takes driver locks that stall the synchronous host calls of this loop by
@@ -366,6 +367,7 @@ def main():
                        "streams": "timed steps: the 3 resblocks of each MRF on 3 streams (fork/join events); the "
                                   "per-kernel roofline pass serialises them so every launch is timed alone",
                        "e2e_timer": "host perf_counter around synchronous calls"},
+            "ms_per_step_median": step_ms[len(step_ms) // 2], "ms_per_step_best": step_ms[0],
             "tflops_per_gpu": flops_step * steps / (dev_ms_max / 1e3) / 1e12,
             "e2e": {"value": e2e_val, "unit": UNIT,
                     "h2d_bytes_per_step": int(mel_host.numel() * 4),

@@ -140,7 +140,11 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
  * synchronises and returns a JSON array, one entry per kernel label:
  *   [{"kernel":"mrf0","launches":18,"ms":..,"flops":..,"bytes":..}, ...]
  * (flops / bytes are the ALGORITHMIC work of those launches).  Call with
- * buf == NULL to query the size.  Used by bench.py for the roofline figures. */
+ * buf == NULL to query the size.  Used by bench.py for the roofline figures.
+ * enable = 1: per launch; the launches of a forward are serialised on the
+ *   caller's stream so that every kernel is timed alone.
+ * enable = 2: per stage ("head", "ups<i>", "mrf<i>", "tail"), with the
+ *   resblocks of each MRF running concurrently as in a normal forward. */
 int hfg_set_profiling(hfg_handle* h, int32_t enable);
 int hfg_get_profile(hfg_handle* h, char* buf, size_t buf_bytes, size_t* needed);
 

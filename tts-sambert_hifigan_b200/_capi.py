@@ -198,8 +198,9 @@ class Handle:
     def set_mel_layout(self, frames_last: bool):
         self._check(self._lib.hfg_set_mel_layout(self._h, 1 if frames_last else 0))
 
-    def set_profiling(self, on: bool):
-        self._check(self._lib.hfg_set_profiling(self._h, 1 if on else 0))
+    def set_profiling(self, on):
+        """False/0 off, True/1 per launch (serialised), 2 per stage (concurrent resblocks)."""
+        self._check(self._lib.hfg_set_profiling(self._h, int(on)))
 
     def get_profile(self):
         import json

@@ -544,7 +544,7 @@ int hfg_set_mel_layout(hfg_handle* h, int32_t layout) {
 
 int hfg_set_profiling(hfg_handle* h, int32_t enable) {
     if (!h) return HFG_ERR_INVALID;
-    h->profiling = enable != 0;
+    h->profiling = enable == 2 ? 2 : (enable != 0 ? 1 : 0);
     return HFG_OK;
 }
 

@@ -91,7 +91,7 @@ struct hfg_handle {
 
     // optional per-launch timing (hfg_set_profiling): one event pair per launch
     struct ProfRec { std::string label; double flops; double bytes; cudaEvent_t e0, e1; };
-    bool profiling = false;
+    int profiling = 0;        // 0 off, 1 per launch (launches serialised), 2 per stage (streams stay on)
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> event_pool;
     size_t events_used = 0;
@@ -103,16 +103,27 @@ struct hfg_handle {
         }
         return event_pool[events_used++];
     }
+    // stage-level records (profiling == 2): events on the caller's stream around a group of launches
+    void stage_begin(cudaStream_t st, const char* label) {
+        if (profiling != 2) return;
+        ProfRec r{label, 0.0, 0.0, next_event(), next_event()};
+        hfg::check_cuda(cudaEventRecord(r.e0, st), "cudaEventRecord");
+        prof.push_back(r);
+    }
+    void stage_end(cudaStream_t st) {
+        if (profiling != 2) return;
+        hfg::check_cuda(cudaEventRecord(prof.back().e1, st), "cudaEventRecord");
+    }
     // call before / after a launch
     void prof_begin(cudaStream_t st, const char* label, double flops, double bytes) {
         launches++;
-        if (!profiling) return;
+        if (profiling != 1) return;
         ProfRec r{label, flops, bytes, next_event(), next_event()};
         hfg::check_cuda(cudaEventRecord(r.e0, st), "cudaEventRecord");
         prof.push_back(r);
     }
     void prof_end(cudaStream_t st) {
-        if (!profiling) return;
+        if (profiling != 1) return;
         hfg::check_cuda(cudaEventRecord(prof.back().e1, st), "cudaEventRecord");
     }
 

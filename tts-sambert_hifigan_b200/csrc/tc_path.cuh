@@ -443,6 +443,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     const int n_rb = h->cfg.num_resblocks;
     auto ptr = [&](const TcPlane& p) { return reinterpret_cast<uint8_t*>(ws + p.off); };
 
+    h->stage_begin(st, "head");
     // ---- zero the padding rows of every plane (one launch) ----
     {
         PadJobs jobs{};
@@ -516,12 +517,14 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
 
     // conv_pre (reference :238); its output is stored as leaky_relu(x) for ups[0] (:244)
     conv(st, h->pre, plan.mel, &plan.pre, nullptr, nullptr, TC_ACC_NONE, "conv_pre");
+    h->stage_end(st);
     dump(0, plan.pre);
 
     const TcPlane* cur = &plan.pre;
     for (size_t i = 0; i < h->ups.size(); ++i) {
         const UpLayer& U = h->ups[i];
         const auto& S = plan.st[i];
+        h->stage_begin(st, ("ups" + std::to_string(i)).c_str());
         {   // x = ups[i](leaky_relu(x)) as u polyphase convolutions (reference :245)
             TcConvArgs a{};
             a.a = ptr(*cur); a.a_bstride = cur->bstride; a.a_pstride = cur->pstride; a.a_nchunks = cur->nchunks;
@@ -543,13 +546,15 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                                  (double)ESZ * U.cin * U.cout * U.k;
             tc_launch_conv<BF16>(h, st, a, B, U.cout, ("ups" + std::to_string(i)).c_str(), flops, bytes);
         }
+        h->stage_end(st);
         dump(1 + 2 * (int)i, S.X);
 
+        h->stage_begin(st, ("mrf" + std::to_string(i)).c_str());
         // MRF (reference :116-131).  The resblocks only meet in the running sum, so resblock j is enqueued on
         // stream j % n_streams: the tail of one kernel (persistent grids rarely divide evenly: 96 tile pairs
         // on 74 clusters in stage 0) is filled by the next resblock's CTAs.  Per-launch profiling serialises
         // everything on `st` so that each kernel is timed alone.
-        const int n_streams = (h->profiling || n_rb < 2) ? 1 : std::max(1, std::min({env_int("HFG_TC_STREAMS", 3),
+        const int n_streams = (h->profiling == 1 || n_rb < 2) ? 1 : std::max(1, std::min({env_int("HFG_TC_STREAMS", 3),
                                                                                       (int)hfg_handle::kStreams, n_rb}));
         // Stream assignment, measured at the bench workload (profiles/r1_tuning.md section 8; ms/step bf16 / tf32):
         // one stream 2.49 / 4.38; three streams, resblocks in natural order with the SHORT ones (k = 3, 7) on
@@ -616,6 +621,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                 check_cuda(cudaStreamWaitEvent(st, h->ev_join[s - 1], 0), "cudaStreamWaitEvent(join)");
             }
         }
+        h->stage_end(st);
         cur = &S.Y;
         dump(2 + 2 * (int)i, S.Y);
     }
@@ -623,11 +629,13 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     {
         const int Tw = cur->T;
         dim3 grid((Tw + 255) / 256, B);
+        h->stage_begin(st, "tail");
         h->prof_begin(st, "conv_post", 2.0 * h->post_cin * 7 * (double)B * Tw,
                       (double)B * Tw * (ESZ * h->post_cin + 4.0));
         tc_conv_post_tanh<BF16><<<grid, 256, sizeof(float) * h->post_cin * 7, st>>>(
             ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 7, 3, cur->bstride, cur->pstride);
         h->prof_end(st);
+        h->stage_end(st);
         check_cuda(cudaGetLastError(), "tc_conv_post_tanh launch");
     }
     (void)CW;
@@ -658,8 +666,8 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     a.acc_mode = TC_ACC_NONE; a.div = 1.f;
     a.n_q = T; a.T_out = T; a.taps_max = L.k; a.k = L.k; a.u = 1; a.dil = L.dil; a.pad = L.pad; a.phases = 1;
     a.out_stride = 1; a.out_off = 0; a.min_off = -L.pad; a.slope = 0.1f;
-    const bool was = h->profiling;
-    h->profiling = false;
+    const int was = h->profiling;
+    h->profiling = 0;
     cudaEvent_t e0, e1;
     check_cuda(cudaEventCreate(&e0), "event"); check_cuda(cudaEventCreate(&e1), "event");
     const PairGeom g = tc_pair_geometry(h, P, in.nchunks, BF16);
