@@ -58,6 +58,7 @@ struct UpLayer {
     float* w_fp32 = nullptr;  // [u][taps_max][cin_pad][cout_pad]
     float* bias = nullptr;
     TcPack tc;
+    TcPack tc_stack;          // the u polyphase tap sets stacked along N (u * cout virtual output channels)
 };
 
 struct PairLayers {

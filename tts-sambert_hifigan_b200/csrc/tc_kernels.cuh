@@ -63,6 +63,7 @@ struct TcConvArgs {
     int T_out;          // valid output rows
     int taps_max, k, u, dil, pad, phases;
     int out_stride, out_off;   // t = q*out_stride + phase + out_off
+    int stack_cout;     // > 0: polyphase tap sets stacked along N -- virtual channel v = phase * stack_cout + channel
     int min_off;        // smallest input row offset over taps
     int R;              // rows per A stage = MT*128 + span
     int sa, sw;         // ring depths
@@ -384,7 +385,8 @@ tc_conv_kernel(const TcConvArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < N; i += (int)blockDim.x - 64) sBias[i] = a.bias[ntile * N + i];
+        for (int i = threadIdx.x - 64; i < N; i += (int)blockDim.x - 64)
+            sBias[i] = a.bias[a.stack_cout ? (ntile * N + i) % a.stack_cout : ntile * N + i];
     }
     tc_fence_before();
     __syncthreads();
@@ -485,13 +487,7 @@ tc_conv_kernel(const TcConvArgs a) {
         const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         for (int mt = 0; mt < MT; ++mt) {
             const int q = q0 + mt * 128 + qlane;
-            const int t = q * a.out_stride + phase + a.out_off;
-            const bool valid = (q < a.n_q) && (t >= 0) && (t < a.T_out);
-            const long long row_bytes = (long long)(kPadL + t) * 16;
             const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * N);
-            const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
-            uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
-            uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
             // launched with 4 or 8 epilogue warps (blockDim 192 / 320): with 8, the two warps of a TMEM lane
             // quarter alternate 32-column steps
             const int col_step = 32 * (((int)blockDim.x - 64) / 128);
@@ -501,7 +497,15 @@ tc_conv_kernel(const TcConvArgs a) {
                 tmem_ld16(tbase + (uint32_t)c0, r0);
                 if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
                 float x0[16], x1[16], p0[16], p1[16];
-                const int ch0 = ntile * N + c0;             // first output channel of this step
+                int ch0 = ntile * N + c0;                   // first output channel of this step
+                int ph = phase;
+                if (a.stack_cout) { ph = ch0 / a.stack_cout; ch0 -= ph * a.stack_cout; }   // a step never straddles phases
+                const int t = q * a.out_stride + ph + a.out_off;
+                const bool valid = (q < a.n_q) && (t >= 0) && (t < a.T_out);
+                const long long row_bytes = (long long)(kPadL + t) * 16;
+                const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
+                uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
                 if (valid && a.res) {
                     load_cells16<BF16>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
                     if (two) load_cells16<BF16>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);

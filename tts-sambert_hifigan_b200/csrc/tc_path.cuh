@@ -133,10 +133,19 @@ inline void tc_pack_conv(hfg_handle* h, ConvLayer& L, const HostTensor& w, const
 }
 inline void tc_pack_up(hfg_handle* h, UpLayer& L, const HostTensor& w, const HostTensor&) {
     const int cout = L.cout, k = L.k, u = L.u;
-    tc_pack_generic(h, L.tc, L.cin, L.cout, L.u, L.taps_max, [&](int n, int ci, int ph, int tap) {
+    auto get = [&](int n, int ci, int ph, int tap) {
         const int j = ph + tap * u;                                     // ConvTranspose1d weight [C_in, C_out, k]
         return j < k ? w.data[((size_t)ci * cout + n) * k + j] : 0.f;
-    });
+    };
+    tc_pack_generic(h, L.tc, L.cin, L.cout, L.u, L.taps_max, get);
+    // Phases stacked along N: every phase multiplies the SAME activation rows (x[q - tap]) by its own tap
+    // set, so the u phase-GEMMs are one GEMM with u * cout virtual output channels -- the activation tile is
+    // loaded once instead of once per phase and the MMAs are u times wider.  A 32-column epilogue step must
+    // not straddle two phases, hence cout % 32 == 0.
+    L.tc_stack.ok = false;
+    if (L.tc.ok && u > 1 && cout % 32 == 0 && tc_pick_n(u * cout) >= cout && (u * cout <= 128 || env_int("HFG_TC_UPS_STACK", 0)))
+        tc_pack_generic(h, L.tc_stack, L.cin, u * cout, 1, L.taps_max,
+                        [&](int nv, int ci, int, int tap) { return get(nv % cout, ci, nv / cout, tap); });
 }
 inline void tc_pack_post(hfg_handle*, const HostTensor&, const HostTensor&) {}   // conv_post reuses post_w
 
@@ -528,23 +537,29 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         {   // x = ups[i](leaky_relu(x)) as u polyphase convolutions (reference :245)
             TcConvArgs a{};
             a.a = ptr(*cur); a.a_bstride = cur->bstride; a.a_pstride = cur->pstride; a.a_nchunks = cur->nchunks;
-            a.N = tc_pick_n(U.cout);
-            a.w = reinterpret_cast<const uint8_t*>(BF16 ? U.tc.w_bf16 : U.tc.w_tf32);
-            const int n_kb = (cur->nchunks + 7) / 8;
+            // measured (bench workload, us, unstacked -> stacked): u = 2 stages tf32 71 -> 68 and 81 -> 61, bf16
+            // 45 -> 41 and 38 -> 42; u = 8 stages (N tiles of 256 either way) 100 -> 104 / no change: stack where
+            // the virtual width u * cout fits one N <= 128 tile
+            const bool stack = U.tc_stack.ok && env_int("HFG_TC_UPS_STACK", U.u * U.cout <= 128 ? 1 : 0);
+            const int cout_v = stack ? U.u * U.cout : U.cout;          // (virtual) output channels of the GEMM
+            a.N = tc_pick_n(cout_v);
+            a.w = reinterpret_cast<const uint8_t*>(stack ? (BF16 ? U.tc_stack.w_bf16 : U.tc_stack.w_tf32)
+                                                         : (BF16 ? U.tc.w_bf16 : U.tc.w_tf32));
             a.w_ntile_stride = (long long)cur->nchunks * U.taps_max * a.N * 16;
-            a.w_phase_stride = a.w_ntile_stride * (U.cout / a.N);
+            a.w_phase_stride = stack ? 0 : a.w_ntile_stride * (U.cout / a.N);
+            a.stack_cout = stack ? U.cout : 0;
             a.bias = U.bias;
             a.out = ptr(S.X); a.res = nullptr; a.o_bstride = S.X.bstride; a.o_pstride = S.X.pstride;
             a.acc_mode = TC_ACC_NONE; a.div = 1.f;
             a.T_out = S.X.T;
             a.n_q = (S.X.T - 1 + U.p) / U.u + 1;
-            a.taps_max = U.taps_max; a.k = U.k; a.u = U.u; a.dil = -1; a.pad = 0; a.phases = U.u;
+            a.taps_max = U.taps_max; a.k = U.k; a.u = U.u; a.dil = -1; a.pad = 0; a.phases = stack ? 1 : U.u;
             a.out_stride = U.u; a.out_off = -U.p; a.min_off = -(U.taps_max - 1);
             a.slope = slope;
             const double flops = 2.0 * U.cin * U.cout * U.k * (double)B * cur->T;
             const double bytes = (double)B * ESZ * ((double)U.cin * cur->T + (double)U.cout * S.X.T) +
                                  (double)ESZ * U.cin * U.cout * U.k;
-            tc_launch_conv<BF16>(h, st, a, B, U.cout, ("ups" + std::to_string(i)).c_str(), flops, bytes);
+            tc_launch_conv<BF16>(h, st, a, B, cout_v, ("ups" + std::to_string(i)).c_str(), flops, bytes);
         }
         h->stage_end(st);
         dump(1 + 2 * (int)i, S.X);
