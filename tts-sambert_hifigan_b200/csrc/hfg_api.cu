@@ -7,6 +7,7 @@
 #include <array>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -528,7 +529,48 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
     const float* src = mel_host;
     if (!mel_pinned) { memcpy(h->pin_mel, mel_host, mel_bytes); src = h->pin_mel; }
     check_cuda(cudaMemcpyAsync(h->dev_mel, src, mel_bytes, cudaMemcpyHostToDevice, h->stream), "H2D mel");
-    do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+    // First call with a given geometry: plain launches (lazy initialisation happens here).  Second call:
+    // the same sequence is captured into a graph.  From then on: one cudaGraphLaunch per forward.
+    auto& G = h->host_graph;
+    static const bool graphs_on = []() { const char* e = getenv("HFG_HOST_GRAPH"); return !e || atoi(e) != 0; }();
+    const bool same = G.B == batch && G.T == frames && G.mode == mode && G.layout == h->mel_layout &&
+                      G.mel == h->dev_mel && G.wav == h->dev_wav && G.ws == h->dev_ws;
+    if (!same) {
+        const bool failed = G.failed;
+        h->drop_host_graph();
+        G.failed = failed;
+        G.B = batch; G.T = frames; G.mode = mode; G.layout = h->mel_layout;
+        G.mel = h->dev_mel; G.wav = h->dev_wav; G.ws = h->dev_ws;
+    }
+    const bool use_graph = graphs_on && !G.failed && h->profiling == 0;
+    if (use_graph && G.exec) {
+        check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
+        h->launches = G.launches;
+    } else if (use_graph && G.calls >= 1) {
+        cudaGraph_t graph = nullptr;
+        check_cuda(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+        bool ok = true;
+        std::string why;
+        try {
+            do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+        } catch (const std::exception& e) { ok = false; why = e.what(); }
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (ok && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+            G.launches = h->launches;
+            check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
+        } else {
+            // capture not possible here: remember that and run the plain sequence
+            cudaGetLastError();
+            G.exec = nullptr;
+            G.failed = true;
+            do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+        }
+        if (graph) cudaGraphDestroy(graph);
+    } else {
+        do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+    }
+    G.calls++;
     float* dst = wav_pinned ? wav_host : h->pin_wav;
     check_cuda(cudaMemcpyAsync(dst, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
     check_cuda(cudaStreamSynchronize(h->stream), "stream sync");

@@ -158,6 +158,22 @@ struct hfg_handle {
         for (auto& e : ev_sum) { if (e) cudaEventDestroy(e); e = nullptr; }
     }
 
+    // hfg_forward_host: the library owns every device buffer and the stream, so the launch sequence of a
+    // forward (about 50 kernels plus the fork / join events) is captured into a CUDA graph once per
+    // (batch, frames, mode, layout, buffers) and replayed with ONE launch -- the host calls are synchronous,
+    // so the ~0.4 ms of launch calls would otherwise sit on the critical path of every step.
+    struct HostGraph {
+        int B = 0, T = 0, mode = -1, layout = -1, calls = 0;
+        const void *mel = nullptr, *wav = nullptr, *ws = nullptr;
+        int64_t launches = 0;
+        cudaGraphExec_t exec = nullptr;
+        bool failed = false;
+    } host_graph;
+    void drop_host_graph() {
+        if (host_graph.exec) cudaGraphExecDestroy(host_graph.exec);
+        host_graph = HostGraph{};
+    }
+
     // hfg_forward_host resources
     cudaStream_t stream = nullptr;
     float* pin_mel = nullptr; size_t pin_mel_bytes = 0;
@@ -180,6 +196,7 @@ struct hfg_handle {
         return p;
     }
     void free_device_weights() {
+        drop_host_graph();                                  // the captured launches point at these weights
         for (void* p : device_allocs) cudaFree(p);
         device_allocs.clear();
         committed = false;
@@ -209,6 +226,7 @@ struct hfg_handle {
         grow_dev(&dev_ws, dev_ws_bytes, ws_bytes);
     }
     void free_host_path() {
+        drop_host_graph();
         if (pin_mel) cudaFreeHost(pin_mel);
         if (pin_wav) cudaFreeHost(pin_wav);
         if (dev_mel) cudaFree(dev_mel);
