@@ -167,6 +167,29 @@ def test_host_buffer_path_equals_device_path(mode):
     assert np.array_equal(host.numpy(), dev)
 
 
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_host_path_graph_replay_and_invalidation(mode):
+    """hfg_forward_host captures the launch sequence into a CUDA graph on the second call with the same
+    geometry and replays it afterwards: replays must equal the device path bit for bit, survive a
+    geometry change and back, and be dropped when the weights are re-committed."""
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 2), mode)
+    mel_a, mel_b = synth.make_mel(8, 2, 80, 40), synth.make_mel(9, 3, 80, 25)
+    dev_a, dev_b = run(gen, mel_a), run(gen, mel_b)
+    with torch.no_grad():
+        for _ in range(4):                            # plain, capture, replay, replay
+            assert np.array_equal(gen(torch.from_numpy(mel_a)).numpy(), dev_a)
+        for _ in range(3):                            # other geometry: new graph
+            assert np.array_equal(gen(torch.from_numpy(mel_b)).numpy(), dev_b)
+        assert np.array_equal(gen(torch.from_numpy(mel_a)).numpy(), dev_a)
+        other = synth.make_weights(cfg, 5)
+        gen.load_state_dict({k: torch.from_numpy(v) for k, v in other.items()})
+        dev_a2 = run(gen, mel_a)
+        assert not np.array_equal(dev_a2, dev_a)
+        for _ in range(3):
+            assert np.array_equal(gen(torch.from_numpy(mel_a)).numpy(), dev_a2)
+
+
 def test_debug_prints_match_reference(manifest, capsys):
     gen = pkg.HiFiGANGenerator(debug_shapes=True, mode="fp32").to("cuda:0")
     with torch.no_grad():
