@@ -259,6 +259,33 @@ def test_time_chunking_with_halo_equals_unchunked(mode):
     assert float((bad - full).abs().max()) > 1e-6     # the halo is doing real work
 
 
+def test_config3_full_size_batch_is_utterance_independent():
+    """BASELINE.json configs[2] at its full size on one GPU: 256 utterances x 172 frames in bf16 mode
+    (27 TFLOP, ~31 GB of workspace).  Size-independent property: every utterance of the big batch is
+    bit-identical to the same utterance generated in a 16-utterance batch (what each of 8 GPUs would run
+    under utterance sharding), and the log-mel L1 against the fp32 mode stays at the committed level."""
+    from tts_sambert_hifigan_b200 import sharding
+    cfg = synth.DEFAULT_CONFIG
+    sd = synth.make_weights(cfg, 0)
+    gen = make_gen(cfg, sd, "bf16")
+    mel = torch.from_numpy(synth.make_mel(21, 256, 80, 172)).to("cuda:0")
+    with torch.no_grad():
+        big = gen(mel)
+        torch.cuda.synchronize()
+        assert big.shape == (256, 1, 172 * 256) and bool(torch.isfinite(big).all())
+        for r in (0, 3, 7):                            # ranks of an 8-way utterance sharding
+            a, b = sharding.shard_bounds(256, 8, r)
+            part = gen(mel[a:b].contiguous())
+            assert torch.equal(part, big[a:b])
+        del part
+        ref = make_gen(cfg, sd, "fp32")(mel[:8].contiguous())
+    err = float((big[:8] - ref).abs().max())
+    print(f"config3 bf16 vs fp32 mode (first 8 utterances): max-abs {err:.3e}")
+    assert err < 5e-3
+    del gen, big
+    torch.cuda.empty_cache()
+
+
 def test_long_form_against_oracle():
     """Largest single-utterance size the suite runs against the CPU oracle."""
     import oracle
