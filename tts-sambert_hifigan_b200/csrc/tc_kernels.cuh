@@ -70,7 +70,13 @@ struct TcConvArgs {
     int tap_group;      // taps per W stage (small layers: fewer, fatter stages)
     int tiles_per_batch;
     float slope;        // leaky_relu slope fused on the OUTPUT (and inverted on the residual)
+    unsigned long long* timeline;   // tuning only: clock64 stamps of the first 64 CTAs along grid.y, [cta][8 events]
 };
+#define HFG_CONV_TL(ev)                                                                              \
+    do {                                                                                             \
+        if (a.timeline && blockIdx.x == 0 && blockIdx.y < 64 && lane == 0)                            \
+            a.timeline[(size_t)blockIdx.y * 8 + (ev)] = (unsigned long long)clock64();                \
+    } while (0)
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -339,6 +345,7 @@ tc_conv_kernel(const TcConvArgs a) {
     constexpr int CW = BF16 ? 8 : 4;       // channels per 16-byte cell
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) HFG_CONV_TL(0);
     const int N = a.N, MT = a.MT, R = a.R;
     const int nck_max = a.a_nchunks < 8 ? a.a_nchunks : 8;
     const uint32_t a_stage_bytes = (uint32_t)R * nck_max * 16;
@@ -392,6 +399,7 @@ tc_conv_kernel(const TcConvArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 0) HFG_CONV_TL(1);
 
     // Roles are warp-uniform: the whole warp runs the loop nest (so loop counters and
     // descriptors stay in uniform registers) and one elected lane issues the async ops.
@@ -446,6 +454,7 @@ tc_conv_kernel(const TcConvArgs a) {
             const int ksteps = nck >> 1;
             mbar_wait(A_FULL(sa_i), sa_ph);
             tc_fence_after();
+            if (kb == 0) HFG_CONV_TL(2);
             const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
             for (int tap0 = 0; tap0 < taps; tap0 += G) {
                 const int g = (taps - tap0) < G ? (taps - tap0) : G;
@@ -472,12 +481,14 @@ tc_conv_kernel(const TcConvArgs a) {
         }
         if (leader) tc_commit(ACC_FULL);
         __syncwarp();
+        HFG_CONV_TL(3);
     } else {
         // ===================== epilogue: TMEM -> regs -> global =====================
         // 32 columns per step: both TMEM loads, the residual cells and the MRF partial sums are all
         // issued before the first use, so one step pays one memory latency instead of one per 16 bytes.
         mbar_wait(ACC_FULL, 0);
         tc_fence_after();
+        if (warp == 2) HFG_CONV_TL(4);
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;                   // the two warps of a quarter alternate 32-column steps
         const int qlane = quarter * 32 + lane;
@@ -549,12 +560,14 @@ tc_conv_kernel(const TcConvArgs a) {
             }
         }
     }
+    if (warp == 2) HFG_CONV_TL(5);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
+    if (warp == 0) HFG_CONV_TL(6);
 }
 
 // ------------------------------------------------------------------ small helpers

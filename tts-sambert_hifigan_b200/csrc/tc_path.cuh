@@ -246,6 +246,7 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     // tile shape: as many 128-row sub-tiles as TMEM (512 columns) and smem allow
     int MT = std::min(4, 512 / a.N);
     MT = std::min(MT, env_int("HFG_TC_MT", 4));
+    if (a.u > 1) MT = std::min(MT, env_int("HFG_TC_UPS_MT", 4));             // polyphase upsamplers (tuning knob)
     MT = std::max(1, std::min(MT, (a.n_q + 127) / 128));
     int sa = std::min(kMaxSA, n_kb), sw = std::min(kMaxSW, std::max(2, env_int("HFG_TC_SW", 4)));
     const int G = tc_tap_group(a.N, nck_max, a.taps_max);
@@ -265,6 +266,19 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     a.tiles_per_batch = (a.n_q + MT * 128 - 1) / (MT * 128);
     const size_t smem = smem_need(MT, sa, sw);
     dim3 grid(a.phases * (cout / a.N), B * a.tiles_per_batch, 1);
+    // tuning only: HFG_TC_CONV_TIMELINE="<label>:<file>" stamps the phases of the first 64 CTAs of that launch
+    unsigned long long* tl_dev = nullptr;
+    const char* tl_env = getenv("HFG_TC_CONV_TIMELINE");
+    const char* tl_path = nullptr;
+    if (tl_env) {
+        const char* colon = strchr(tl_env, ':');
+        if (colon && (size_t)(colon - tl_env) == strlen(label) && strncmp(tl_env, label, strlen(label)) == 0) {
+            tl_path = colon + 1;
+            check_cuda(cudaMalloc((void**)&tl_dev, 64 * 8 * 8), "cudaMalloc(timeline)");
+            check_cuda(cudaMemsetAsync(tl_dev, 0, 64 * 8 * 8, st), "cudaMemset(timeline)");
+            a.timeline = tl_dev;
+        }
+    }
     h->prof_begin(st, label, flops, bytes);
     // 8 epilogue warps when the CTA owns its SM anyway (big tiles: latency-bound epilogue, profiles/r1_tuning.md);
     // 4 when two CTAs can share the SM (narrow layers), which hides the epilogue better than more warps
@@ -272,6 +286,21 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     tc_conv_kernel<BF16><<<grid, threads, smem, st>>>(a);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_conv_kernel launch");
+    if (tl_dev) {
+        std::vector<unsigned long long> hb(64 * 8);
+        check_cuda(cudaStreamSynchronize(st), "sync(timeline)");
+        check_cuda(cudaMemcpy(hb.data(), tl_dev, 64 * 8 * 8, cudaMemcpyDeviceToHost), "cudaMemcpy(timeline)");
+        cudaFree(tl_dev);
+        if (FILE* f = fopen(tl_path, "a")) {
+            fprintf(f, "# %s N=%d MT=%d sa=%d sw=%d G=%d smem=%zu threads=%d grid=%dx%d\n", label, a.N, a.MT, a.sa, a.sw, a.tap_group,
+                    smem, threads, grid.x, grid.y);
+            for (int i = 0; i < 64; ++i) {
+                for (int e = 0; e < 8; ++e) fprintf(f, "%llu ", hb[i * 8 + e]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
 }
 
 // ---- fused ResBlock pair ----
