@@ -9,6 +9,7 @@
 #include "model.h"
 #include "tc_kernels.cuh"
 #include "tc_pair_kernel.cuh"
+#include "tc_up_kernel.cuh"
 
 namespace hfg {
 
@@ -306,6 +307,66 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
 // ---- fused ResBlock pair ----
 struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; };
 
+// Persistent, double-buffered launch of a plain-epilogue convolution (conv_pre, upsamplers): tc_up_kernel.
+// Returns false when the geometry does not fit (the caller falls back to tc_launch_conv).
+template <bool BF16>
+static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, int cout, const char* label,
+                         double flops, double bytes) {
+    if (a.res || a.acc_mode != TC_ACC_NONE || !a.out || !env_int("HFG_TC_UP_PERSIST", 1)) return false;
+    const int nck_max = std::min(8, a.a_nchunks);
+    const int n_kb = (a.a_nchunks + 7) / 8;
+    const int span = (a.taps_max - 1) * (a.dil < 0 ? -a.dil : a.dil);
+    int MT = std::min(4, 256 / a.N);                                   // two accumulator buffers: 2 * MT * N <= 512 columns
+    if (MT < 1) return false;
+    MT = std::min(MT, env_int("HFG_TC_UP_MT", 4));
+    MT = std::max(1, std::min(MT, (a.n_q + 127) / 128));
+    // one barrier round trip per weight stage (profiles/r1_tuning.md section 6): stages of up to 32 KB
+    const int tap_bytes = a.N * nck_max * 16;
+    const int G = std::min(a.taps_max, std::max(1, env_int("HFG_TC_UP_STAGE_BYTES", 32768) / tap_bytes));
+    a.tap_group = G;
+    // a 256-wide tile leaves one 128-row sub-tile per accumulator buffer: twice the items of the one-shot
+    // kernel and a second, mostly empty round on 148 SMs (ups0: 64 vs 52 us) -- persistent only when
+    // narrower, or when everything fits one round anyway
+    {
+        const int mt1 = std::max(1, std::min(MT, (a.n_q + 127) / 128));
+        const int items = B * ((a.n_q + mt1 * 128 - 1) / (mt1 * 128)) * a.phases * (cout / a.N);
+        if (a.N > 128 && items > h->sm_count && !env_int("HFG_TC_UP_WIDE", 0)) return false;
+    }
+    int sa = std::min(kUpMaxSA, std::max(2, env_int("HFG_TC_UP_SA", 4)));
+    int sw = std::min(kUpMaxSW, std::max(2, env_int("HFG_TC_UP_SW", 4)));
+    auto smem_need = [&](int mt, int sa_, int sw_) {
+        const size_t R = (size_t)mt * 128 + span;
+        return (size_t)sa_ * R * nck_max * 16 + (size_t)sw_ * G * a.N * nck_max * 16 + (size_t)((cout + 3) & ~3) * 4 + 256;
+    };
+    while (smem_need(MT, sa, sw) > (size_t)kTcSmemLimit) {
+        if (sw > 3) --sw;
+        else if (sa > 2) --sa;
+        else if (sw > 2) --sw;
+        else if (MT > 1) MT /= 2;
+        else return false;
+    }
+    (void)n_kb;
+    a.MT = MT; a.sa = sa; a.sw = sw;
+    a.R = MT * 128 + span;
+    a.tiles_per_batch = (a.n_q + MT * 128 - 1) / (MT * 128);
+    TcUpArgs ua{};
+    ua.c = a;
+    ua.n_ctile = cout / a.N;
+    ua.pn_per_tile = a.phases * ua.n_ctile;
+    ua.n_items = B * a.tiles_per_batch * ua.pn_per_tile;
+    ua.cout_total = cout;
+    const size_t smem = smem_need(MT, sa, sw);
+    const int grid = std::min(ua.n_items, h->sm_count);
+    if (env_int("HFG_TC_VERBOSE", 0))
+        fprintf(stderr, "[up] %s N=%d MT=%d G=%d sa=%d sw=%d smem=%zu grid=%d items=%d\n", label, a.N, MT, G, sa, sw, smem,
+                grid, ua.n_items);
+    h->prof_begin(st, label, flops, bytes);
+    tc_up_kernel<BF16><<<grid, kTcThreads, smem, st>>>(ua);
+    h->prof_end(st);
+    check_cuda(cudaGetLastError(), "tc_up_kernel launch");
+    return true;
+}
+
 static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
     // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
     // (profiles/r1_tuning.md sections 5 and 7): every C >= 64 layer, except tf32 C = 256 whose fp32 H tile
@@ -550,7 +611,8 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         const double bytes = (double)B * in.T * ESZ * (L.cin + L.cout * (res ? 2 : 1)) +
                              (acc ? 4.0 * B * in.T * L.cout * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) +
                              (double)ESZ * L.cin * L.cout * L.k;
-        tc_launch_conv<BF16>(h, st, a, B, L.cout, label, flops, bytes);
+        if (!tc_launch_up<BF16>(h, st, a, B, L.cout, label, flops, bytes))
+            tc_launch_conv<BF16>(h, st, a, B, L.cout, label, flops, bytes);
     };
 
     // conv_pre (reference :238); its output is stored as leaky_relu(x) for ups[0] (:244)
@@ -588,7 +650,9 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             const double flops = 2.0 * U.cin * U.cout * U.k * (double)B * cur->T;
             const double bytes = (double)B * ESZ * ((double)U.cin * cur->T + (double)U.cout * S.X.T) +
                                  (double)ESZ * U.cin * U.cout * U.k;
-            tc_launch_conv<BF16>(h, st, a, B, cout_v, ("ups" + std::to_string(i)).c_str(), flops, bytes);
+            const std::string ulab = "ups" + std::to_string(i);
+            if (!tc_launch_up<BF16>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes))
+                tc_launch_conv<BF16>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes);
         }
         h->stage_end(st);
         dump(1 + 2 * (int)i, S.X);
@@ -778,6 +842,7 @@ inline void configure_kernels(hfg_handle*) {
     auto big = [](auto fn) {
         check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     };
+    big(tc_up_kernel<true>); big(tc_up_kernel<false>);
     big(tc_pair_kernel<true, 1, 1>); big(tc_pair_kernel<false, 1, 1>);
     big(tc_pair_kernel<true, 2, 1>); big(tc_pair_kernel<false, 2, 1>);
     big(tc_pair_kernel<true, 1, 2>); big(tc_pair_kernel<false, 1, 2>);
