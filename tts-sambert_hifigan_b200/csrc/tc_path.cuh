@@ -312,7 +312,12 @@ struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ
 template <bool BF16>
 static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, int cout, const char* label,
                          double flops, double bytes) {
-    if (a.res || a.acc_mode != TC_ACC_NONE || !a.out || !env_int("HFG_TC_UP_PERSIST", 1)) return false;
+    if (!env_int("HFG_TC_UP_PERSIST", 1)) return false;
+    const bool plain = !a.res && a.acc_mode == TC_ACC_NONE;
+    // ResBlock convolutions (tf32 C = 256, unfused): measured slower than the one-shot kernel -- 0.77 vs 0.71 ms
+    // for the stage with the resblocks concurrent (a 256-wide tile leaves 128 rows per accumulator buffer and
+    // one-tap weight stages) -- so they stay on tc_conv_kernel unless asked for
+    if (!plain && !env_int("HFG_TC_UP_RESBLOCK", 0)) return false;
     const int nck_max = std::min(8, a.a_nchunks);
     const int n_kb = (a.a_nchunks + 7) / 8;
     const int span = (a.taps_max - 1) * (a.dil < 0 ? -a.dil : a.dil);
@@ -330,7 +335,7 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
     {
         const int mt1 = std::max(1, std::min(MT, (a.n_q + 127) / 128));
         const int items = B * ((a.n_q + mt1 * 128 - 1) / (mt1 * 128)) * a.phases * (cout / a.N);
-        if (a.N > 128 && items > h->sm_count && !env_int("HFG_TC_UP_WIDE", 0)) return false;
+        if (plain && a.N > 128 && items > h->sm_count && !env_int("HFG_TC_UP_WIDE", 0)) return false;
     }
     int sa = std::min(kUpMaxSA, std::max(2, env_int("HFG_TC_UP_SA", 4)));
     int sw = std::min(kUpMaxSW, std::max(2, env_int("HFG_TC_UP_SW", 4)));

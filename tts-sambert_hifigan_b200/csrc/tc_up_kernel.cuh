@@ -1,5 +1,5 @@
-// Persistent implicit-GEMM convolution for the layers with a plain epilogue (bias -> leaky_relu ->
-// store): conv_pre and the polyphase ConvTranspose1d upsamplers (reference models/hifigan.py:238,245).
+// Persistent implicit-GEMM convolution: conv_pre, the polyphase ConvTranspose1d upsamplers and the
+// ResBlock convolutions that do not fit the fused pair kernel (reference models/hifigan.py:80-85,238,245).
 //
 // Same operand layout and tap-shift trick as tc_conv_kernel (tc_kernels.cuh), but:
 //   * one CTA per SM loops over work items (tile, phase, channel tile) instead of one CTA per item, so the
@@ -186,11 +186,15 @@ tc_up_kernel(const TcUpArgs ua) {
             __syncwarp();
         }
     } else {
-        // ===================== epilogue: TMEM -> bias -> leaky_relu -> operand dtype -> global =====================
+        // ===================== epilogue: TMEM -> bias (+ residual, MRF sum) -> leaky_relu -> operand dtype -> global =====================
+        // same arithmetic, in the same order, as tc_conv_kernel's epilogue (bit-identical results)
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;                   // the two warps of a quarter alternate 32-column steps
         const int qlane = quarter * 32 + lane;
-        const float slope = a.slope;
+        const float slope = a.slope, inv_slope = 1.0f / a.slope;
+        const float inv_div = 1.0f / a.div;
+        const bool add_prev = a.acc_mode == TC_ACC_ADD || a.acc_mode == TC_ACC_FINAL;
+        const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         const int col_step = 32 * (n_epi_warps / 4);
         uint32_t it = 0;
         for (int item = item0; item < ua.n_items; item += item_step, ++it) {
@@ -209,24 +213,55 @@ tc_up_kernel(const TcUpArgs ua) {
                     uint32_t r0[16], r1[16];
                     tmem_ld16(tbase + (uint32_t)c0, r0);
                     if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
+                    float x0[16], x1[16], p0[16], p1[16];
                     const int vc0 = ntile * N + c0;             // first (virtual) output channel of this step
                     int ch0 = vc0, ph = phase;
                     if (a.stack_cout) { ph = vc0 / a.stack_cout; ch0 = vc0 - ph * a.stack_cout; }   // a step never straddles phases
                     const int t = q * a.out_stride + ph + a.out_off;
                     const bool valid = (q < a.n_q) && (t >= 0) && (t < a.T_out);
-                    uint8_t* op = a.out + (long long)b * a.o_bstride + (long long)(kPadL + t) * 16;
+                    const long long row_bytes = (long long)(kPadL + t) * 16;
+                    const uint8_t* rp = a.res + (long long)b * a.o_bstride + row_bytes;
+                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                    uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+                    if (valid && a.res) {
+                        load_cells16<BF16>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
+                        if (two) load_cells16<BF16>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
+                    }
+                    if (valid && add_prev) {
+                        load_f32x16(ap + (long long)(ch0 / 4) * a.acc_pstride, a.acc_pstride, p0);
+                        if (two) load_f32x16(ap + (long long)((ch0 + 16) / 4) * a.acc_pstride, a.acc_pstride, p1);
+                    }
                     tmem_ld_wait();
                     if (!valid) continue;
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         if (hh == 1 && !two) break;
+                        const int ch = ch0 + 16 * hh;
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(hh ? r1[i] : r0[i]);
                         add_bias16(v, sBias + vc0 + 16 * hh);
+                        if (a.res) {                             // x + xt   (reference :85)
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                        store_cells16<BF16>(op + (long long)((ch0 + 16 * hh) / CW) * a.o_pstride, a.o_pstride, v);
+                            for (int i = 0; i < 16; ++i) v[i] += lrelu_inv(hh ? x1[i] : x0[i], inv_slope);
+                        }
+                        if (add_prev) {                          // output + rb(x)  (reference :129)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += hh ? p1[i] : p0[i];
+                        }
+                        if (acc_store) {
+                            store_f32x16(ap + (long long)(ch / 4) * a.acc_pstride, a.acc_pstride, v);
+                            if (!a.out) continue;
+                        }
+                        if (a.acc_mode == TC_ACC_FINAL) {        // / len(resblocks)  (reference :131)
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] *= inv_div;
+                        }
+                        if (a.out) {                             // next layer's leaky_relu, operand dtype
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                            store_cells16<BF16>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
+                        }
                     }
                 }
             }
