@@ -98,7 +98,12 @@ int hfg_workspace_bytes(const hfg_handle* h, int32_t batch, int32_t frames, int3
                         size_t* bytes);
 
 /* HiFiGANGenerator.forward (reference models/hifigan.py:224-261):
- * mel_dev fp32 [B, n_mels, Tfrm] contiguous  ->  wav_dev fp32 [B, 1, T_out]. */
+ * mel_dev fp32 [B, n_mels, Tfrm] contiguous  ->  wav_dev fp32 [B, 1, T_out].
+ * Asynchronous: everything is ordered after the work already in `stream` and
+ * before whatever is enqueued on it next.  In the tensor-core modes the three
+ * resblocks of each MRF run on `stream` plus two internal streams of the
+ * handle (fork / join with events, no host synchronisation); the workspace may
+ * be dirty on entry (the pad rows a valid output depends on are re-zeroed). */
 int hfg_forward(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames,
                 float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
                 void* stream);
@@ -124,7 +129,9 @@ int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32
  * host->device, runs forward, copies the waveform back and synchronises.
  * Pinned staging, workspace and stream are owned by the handle and grown on
  * demand.  This is what `module(mel_cpu_tensor)` costs a caller whose data
- * lives on the host. */
+ * lives on the host.  From the second call with the same (batch, frames,
+ * mode, layout) the launch sequence is replayed from a CUDA graph
+ * (environment HFG_HOST_GRAPH=0 turns that off). */
 int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
                      float* wav_host, int32_t mode);
 
