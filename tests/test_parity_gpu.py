@@ -6,6 +6,8 @@ Tolerances (max-abs on the waveform, whose peak is 0.03-0.07 at random init):
   tf32  1e-3   north_star's stated bound for the fp32/TF32 mode
   bf16  5e-3   bf16 operands + bf16 stored activations (log-mel L1 reported by bench)
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -188,6 +190,29 @@ def test_host_path_graph_replay_and_invalidation(mode):
         assert not np.array_equal(dev_a2, dev_a)
         for _ in range(3):
             assert np.array_equal(gen(torch.from_numpy(mel_a)).numpy(), dev_a2)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_kernel_variants_are_bit_identical(mode):
+    """The launch plan picks between kernels that implement the same arithmetic in the same order
+    (persistent vs one-shot conv kernel, polyphase phases stacked along N or one phase per CTA, fused pair
+    vs two convolutions, one stream vs three).  The knobs are read once per process, so each variant runs
+    in its own interpreter; all outputs must hash identically."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    variants = [{}, {"HFG_TC_UP_PERSIST": "0"}, {"HFG_TC_UP_PERSIST": "0", "HFG_TC_UPS_STACK": "0"},
+                {"HFG_TC_UPS_STACK": "1"}, {"HFG_TC_UP_RESBLOCK": "1", "HFG_TC_UP_WIDE": "1"},
+                {"HFG_TC_STREAMS": "1"}, {"HFG_TC_PAIR_CTAS": "1"}]
+    hashes = []
+    for v in variants:
+        env = dict(os.environ, **v)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
+                             env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
+        hashes.append(line.split()[1])
+        print(v, line)
+    assert len(set(hashes)) == 1, list(zip(variants, hashes))
 
 
 def test_debug_prints_match_reference(manifest, capsys):

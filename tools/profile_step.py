@@ -1,10 +1,15 @@
-"""One warm-up forward + one forward of the bench workload, for ncu captures:
+"""One warm-up forward + one forward of the bench workload, for ncu captures.
 
-    ncu --set full -k regex:tc_conv_kernel -s <77 + idx> -c 1 ... python tools/profile_step.py --mode bf16
+Launch order inside one forward (default config; ncu serialises the three streams in enqueue order):
+  zero_pads, pack_mel, conv_pre, then per stage i: ups{i}, and the MRF as
+  k3 pair0, k3 pair1, k7 pair0, k7 pair1, k11 pair0, k11 pair1, k3 pair2, k7 pair2, k11 pair2
+  (pair l = dilation 1, 3, 5; in tf32 mode stage 0 is unfused: two tc_conv_kernel launches per pair),
+  finally conv_post.  53 launches in tf32, 44 in bf16.
 
-tc_conv_kernel launch order inside one forward (default config):
-  0 conv_pre | 1 ups0 | 2..19 mrf0 | 20 ups1 | 21..38 mrf1 | 39 ups2 | 40..57 mrf2 | 58 ups3 | 59..76 mrf3
-  inside an MRF: resblock j (k = 3, 7, 11) x pair l (d = 1, 3, 5) x (conv1, conv2) -> offset 6 j + 2 l + c
+    # mrf1.k11 pair 0 (dominant kernel), second forward: 9 fused launches per stage
+    ncu --set full -k regex:tc_pair_kernel -s 31 -c 1 ... python tools/profile_step.py --mode tf32   # 27 + 4
+    ncu --set full -k regex:tc_pair_kernel -s 49 -c 1 ... python tools/profile_step.py --mode bf16   # 36 + 9 + 4
+    tools/ncu_forward.sh tf32 53        # every kernel of the second forward, light metric set
 """
 import argparse
 import os
