@@ -445,7 +445,7 @@ tc_conv_kernel(const TcConvArgs a) {
         const uint32_t idesc = umma_idesc<BF16>(N);
         // descriptor high words are loop-invariant; the low word is start>>4 | LBO>>4 << 16,
         // so stepping K chunks / sub-tiles / taps is an add of (bytes >> 4) = rows on the low word
-        const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;        // SBO = 128 B, version 1
+        const uint32_t a_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1 (A and B)
         const uint32_t a_lbo = ((uint32_t)R) << 16, b_lbo = ((uint32_t)N) << 16;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t acc_on = 0;

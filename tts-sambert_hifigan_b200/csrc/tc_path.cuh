@@ -598,7 +598,6 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         a.a = ptr(in); a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
         a.N = tc_pick_n(L.cout);
         a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
-        const int n_kb = (in.nchunks + 7) / 8;
         a.w_ntile_stride = (long long)in.nchunks * L.k * a.N * 16;
         a.w_phase_stride = 0;
         a.bias = L.bias;
