@@ -358,7 +358,9 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
     ua.c = a;
     ua.n_ctile = cout / a.N;
     ua.pn_per_tile = a.phases * ua.n_ctile;
-    ua.n_items = B * a.tiles_per_batch * ua.pn_per_tile;
+    const long long n_items = (long long)B * a.tiles_per_batch * ua.pn_per_tile;
+    if (n_items > 0x7fffffffLL) return false;                          // item index is an int in the kernel
+    ua.n_items = (int)n_items;
     ua.cout_total = cout;
     const size_t smem = smem_need(MT, sa, sw);
     const int grid = std::min(ua.n_items, h->sm_count);
