@@ -64,7 +64,9 @@ typedef enum hfg_status {
 typedef enum hfg_mode {
     HFG_MODE_FP32 = 0,  /* fp32 FFMA kernels, fp32 activations: strict parity mode      */
     HFG_MODE_TF32 = 1,  /* tcgen05 kind::tf32, fp32 activations (parity <= 1e-3)          */
-    HFG_MODE_BF16 = 2   /* tcgen05 kind::f16 (bf16 operands), bf16 activations, fp32 acc  */
+    HFG_MODE_BF16 = 2,  /* tcgen05 kind::f16 (bf16 operands), bf16 activations, fp32 acc  */
+    HFG_MODE_FP16 = 3   /* tcgen05 kind::f16 (fp16 operands), fp16 activations, fp32 acc: tf32's 10-bit
+                           mantissa at bf16's MMA rate; conversions saturate at +-65504 (parity <= 1e-3) */
 } hfg_mode;
 
 int hfg_abi_version(void);

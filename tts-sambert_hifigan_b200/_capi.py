@@ -7,7 +7,8 @@ from typing import Dict, Optional, Sequence
 
 HFG_MAX_STAGES = 8
 MODE_FP32, MODE_TF32, MODE_BF16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16}
+MODE_FP16 = 3
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32, "bf16": MODE_BF16, "fp16": MODE_FP16}
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_WORKSPACE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 

@@ -11,6 +11,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libhfg_b200.so")
+# Same sources with -DHFG_TUNING: HFG_TC_* environment knobs, clock64 timelines and the "switch parts of the
+# kernel off" experiments exist only in this build (tools/, kernel-variant tests; loaded via HFG_LIB_PATH).
+LIB_TUNING = os.path.join(LIB_DIR, "libhfg_b200_tuning.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -29,27 +32,33 @@ def _deps():
         + glob.glob(os.path.join(INCLUDE, "*.h"))
 
 
-def is_stale() -> bool:
-    if not os.path.exists(LIB):
+def is_stale(lib: str = LIB) -> bool:
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(p) > t for p in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
-        return LIB
+def _compile(lib: str, extra, verbose: bool):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
-        raise RuntimeError("nvcc not found: cannot build libhfg_b200.so")
+        raise RuntimeError(f"nvcc not found: cannot build {os.path.basename(lib)}")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + _sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libhfg_b200.so")
+        raise RuntimeError(f"nvcc failed building {os.path.basename(lib)}")
+
+
+def build(force: bool = False, verbose: bool = False, tuning: bool = True) -> str:
+    """Production library, and (tuning=True) the instrumented build next to it."""
+    if force or is_stale(LIB):
+        _compile(LIB, [], verbose)
+    if tuning and (force or is_stale(LIB_TUNING)):
+        _compile(LIB_TUNING, ["-DHFG_TUNING"], False)
     return LIB
 
 

@@ -354,7 +354,7 @@ static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
     if (B > 65535) throw StatusError(HFG_ERR_INVALID, "batch > 65535: split the call");
     size_t need_bytes = 0;
     if (mode == HFG_MODE_FP32) need_bytes = workspace_fp32(h, B, T);
-    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) need_bytes = tc_workspace_bytes(h, B, T, mode);
+    else if (tc_is_tc_mode(mode)) need_bytes = tc_workspace_bytes(h, B, T, mode);
     else throw StatusError(HFG_ERR_INVALID, "unknown mode");
     if (!ws || ws_bytes < need_bytes) throw StatusError(HFG_ERR_WORKSPACE, "workspace too small");
     if (((uintptr_t)ws & 255) != 0) throw StatusError(HFG_ERR_WORKSPACE, "workspace must be 256-byte aligned");
@@ -482,7 +482,7 @@ int hfg_workspace_bytes(const hfg_handle* hc, int32_t batch, int32_t frames, int
     if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
     if (batch <= 0 || frames <= 0) throw StatusError(HFG_ERR_INVALID, "batch and frames must be positive");
     if (mode == HFG_MODE_FP32) *bytes = workspace_fp32(h, batch, frames);
-    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) *bytes = tc_workspace_bytes(h, batch, frames, mode);
+    else if (tc_is_tc_mode(mode)) *bytes = tc_workspace_bytes(h, batch, frames, mode);
     else throw StatusError(HFG_ERR_INVALID, "unknown mode");
     HFG_CATCH(h)
 }
@@ -522,7 +522,7 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
     const size_t wav_bytes = sizeof(float) * (size_t)batch * tout;
     size_t ws_bytes = 0;
     if (mode == HFG_MODE_FP32) ws_bytes = workspace_fp32(h, batch, frames);
-    else if (mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16) ws_bytes = tc_workspace_bytes(h, batch, frames, mode);
+    else if (tc_is_tc_mode(mode)) ws_bytes = tc_workspace_bytes(h, batch, frames, mode);
     else throw StatusError(HFG_ERR_INVALID, "unknown mode");
     const bool mel_pinned = (flags & HFG_HOST_MEL_PINNED) != 0, wav_pinned = (flags & HFG_HOST_WAV_PINNED) != 0;
     h->ensure_host_path(mel_pinned ? 0 : mel_bytes, wav_pinned ? 0 : wav_bytes, mel_bytes, wav_bytes, ws_bytes);
@@ -628,8 +628,9 @@ int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair
         pair < 0 || pair >= (int)h->mrfs[stage][resblock].size() || which < 0 || which > 2 || batch <= 0 ||
         rows <= 0 || iters <= 0)
         throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: bad argument");
-    if (mode == HFG_MODE_BF16) *ms = tc_bench_layer_impl<true>(h, stage, resblock, pair, which, batch, rows, iters);
-    else if (mode == HFG_MODE_TF32) *ms = tc_bench_layer_impl<false>(h, stage, resblock, pair, which, batch, rows, iters);
+    if (mode == HFG_MODE_BF16) *ms = tc_bench_layer_impl<PREC_BF16>(h, stage, resblock, pair, which, batch, rows, iters);
+    else if (mode == HFG_MODE_FP16) *ms = tc_bench_layer_impl<PREC_FP16>(h, stage, resblock, pair, which, batch, rows, iters);
+    else if (mode == HFG_MODE_TF32) *ms = tc_bench_layer_impl<PREC_TF32>(h, stage, resblock, pair, which, batch, rows, iters);
     else throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: tensor-core modes only");
     HFG_CATCH(h)
 }

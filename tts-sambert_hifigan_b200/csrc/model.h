@@ -36,11 +36,11 @@ struct HostTensor {
 // Tensor-core operand pack of one conv (tc_path.cuh): per tap, an [N=Cout][K=Cin]
 // K-major matrix in the UMMA no-swizzle "interleaved" canonical layout.
 struct TcPack {
-    void* w_bf16 = nullptr;   // bf16 operand tiles
-    void* w_tf32 = nullptr;   // fp32 (consumed as tf32) operand tiles
-    // fused-pair kernel packs: [bf16 ? 1 : 0][N-halves for a cta_group::2 pair ? 1 : 0][K block of 4 cells ? 1 : 0]
-    void* w_pair[2][2][2] = {};
-    long long half_stride[2][2] = {};     // [bf16][kbc4]: bytes between the two N-halves
+    // indexed by operand precision (tc_kernels.cuh: PREC_TF32 = 0 fp32 cells consumed as tf32, PREC_BF16 = 1, PREC_FP16 = 2)
+    void* w[3] = {};          // operand tiles of the plain conv kernels
+    // fused-pair kernel packs: [precision][N-halves for a cta_group::2 pair ? 1 : 0][K block of 4 cells ? 1 : 0]
+    void* w_pair[3][2][2] = {};
+    long long half_stride[3][2] = {};     // [precision][kbc4]: bytes between the two N-halves
     bool ok = false;          // layer shape is covered by the tensor-core path
 };
 
@@ -77,6 +77,7 @@ struct hfg_handle {
     int64_t launches = 0;
     int mel_layout = 0;       // 0 = [B, n_mels, T] (reference), 1 = [B, T, n_mels] (acoustic-model output)
     unsigned long long* pair_timeline = nullptr;   // tuning only: phase stamps of the fused pair kernel (hfg_bench_layer)
+    int pair_regs[3][2][2] = {};                   // registers per thread of tc_pair_kernel<P, MINB, CTAS> (occupancy), filled lazily
 
     std::map<std::string, hfg::HostTensor> sd;   // raw state_dict as set by the caller
 

@@ -32,6 +32,7 @@
 // polyphase convolutions whose outputs interleave with stride u.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -43,6 +44,27 @@ constexpr int kPadL = 32;          // zero rows in front of t = 0 in every plane
 constexpr int kMaxSA = 2, kMaxSW = 8;
 
 enum : int { TC_ACC_NONE = 0, TC_ACC_WRITE = 1, TC_ACC_ADD = 2, TC_ACC_FINAL = 3 };
+
+// Operand precision of a tensor-core mode (template parameter P of every kernel below):
+//   PREC_TF32  fp32 storage, tcgen05 kind::tf32             (4 channels per 16-byte cell)
+//   PREC_BF16  bf16 storage, tcgen05 kind::f16, bf16 x bf16 (8 channels per cell)
+//   PREC_FP16  fp16 storage, tcgen05 kind::f16, fp16 x fp16 (8 channels per cell): the 10-bit mantissa of
+//              tf32 at the MMA rate and operand bytes of bf16; conversions saturate to +-65504
+// Accumulation is fp32 in TMEM in every mode.
+enum : int { PREC_TF32 = 0, PREC_BF16 = 1, PREC_FP16 = 2 };
+template <int P> struct Prec {
+    static constexpr int CW = P == PREC_TF32 ? 4 : 8;     // channels per 16-byte cell
+    static constexpr int ESZ = P == PREC_TF32 ? 4 : 2;    // bytes per stored element
+};
+
+// Tuning instrumentation (clock64 timelines, "switch parts of the kernel off" experiments, HFG_TC_* environment
+// knobs) exists only in builds with -DHFG_TUNING (lib/libhfg_b200_tuning.so); the production library has none
+// of it, so a stray environment variable cannot change kernel selection or results.
+#ifdef HFG_TUNING
+#define HFG_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define HFG_DBG(a, bit) 0
+#endif
 
 struct TcConvArgs {
     // A operand: plane(b, chunk) = a + b*a_bstride + chunk*a_pstride; row r at +16 r
@@ -72,11 +94,15 @@ struct TcConvArgs {
     float slope;        // leaky_relu slope fused on the OUTPUT (and inverted on the residual)
     unsigned long long* timeline;   // tuning only: clock64 stamps of the first 64 CTAs along grid.y, [cta][8 events]
 };
+#ifndef HFG_TUNING
+#define HFG_CONV_TL(ev) do { } while (0)
+#else
 #define HFG_CONV_TL(ev)                                                                              \
     do {                                                                                             \
         if (a.timeline && blockIdx.x == 0 && blockIdx.y < 64 && lane == 0)                            \
             a.timeline[(size_t)blockIdx.y * 8 + (ev)] = (unsigned long long)clock64();                \
     } while (0)
+#endif
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -188,16 +214,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes,
            ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // UMMA instruction descriptor: fp32 accumulate, K-major A and B, M = 128
-template <bool BF16>
+template <int P>
 __device__ __forceinline__ uint32_t umma_idesc(int N, int M = 128) {
-    const uint32_t fmt = BF16 ? 1u : 2u;            // 1 = BF16, 2 = TF32
+    const uint32_t fmt = P == PREC_BF16 ? 1u : (P == PREC_FP16 ? 0u : 2u);   // kind::f16: 0 = F16, 1 = BF16; kind::tf32: 2 = TF32
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // cta_group::2: one instruction drives the tensor cores of both SMs of a CTA pair (M = 256: each CTA
 // supplies its own 128 rows of A and HALF of the N rows of B from the same smem offsets)
-template <bool BF16>
+template <int P>
 __device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (BF16) {
+    if constexpr (P != PREC_TF32) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -209,9 +235,9 @@ __device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t adesc, uint64_t 
             ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
     }
 }
-template <bool BF16>
+template <int P>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if constexpr (BF16) {
+    if constexpr (P != PREC_TF32) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -226,23 +252,23 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
 // One (tap, sub-tile): `ksteps` K-steps of UMMA_K (two 16-byte cells each), A and B descriptors
 // advanced by 2 cells per step.  The common 4-step case is straight-line code so the
 // UTCHMMAs issue back to back from uniform registers.
-template <bool BF16, int CTAS = 1>
+template <int P, int CTAS = 1>
 __device__ __forceinline__ void umma_any(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-    if constexpr (CTAS == 2) umma2<BF16>(d, ad, bd, idesc, acc);
-    else umma<BF16>(d, ad, bd, idesc, acc);
+    if constexpr (CTAS == 2) umma2<P>(d, ad, bd, idesc, acc);
+    else umma<P>(d, ad, bd, idesc, acc);
 }
-template <bool BF16, int CTAS = 1>
+template <int P, int CTAS = 1>
 __device__ __forceinline__ void umma_ksteps(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo,
                                             uint32_t a_step, uint32_t b_step, uint32_t idesc, int ksteps,
                                             uint32_t acc_first) {
     if (ksteps == 4) {
-        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first);
-        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + a_step), ((uint64_t)hi << 32) | (b_lo + b_step), idesc, 1u);
-        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 2 * a_step), ((uint64_t)hi << 32) | (b_lo + 2 * b_step), idesc, 1u);
-        umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 3 * a_step), ((uint64_t)hi << 32) | (b_lo + 3 * b_step), idesc, 1u);
+        umma_any<P, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first);
+        umma_any<P, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + a_step), ((uint64_t)hi << 32) | (b_lo + b_step), idesc, 1u);
+        umma_any<P, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 2 * a_step), ((uint64_t)hi << 32) | (b_lo + 2 * b_step), idesc, 1u);
+        umma_any<P, CTAS>(d_tmem, ((uint64_t)hi << 32) | (a_lo + 3 * a_step), ((uint64_t)hi << 32) | (b_lo + 3 * b_step), idesc, 1u);
     } else {
         for (int s = 0; s < ksteps; ++s) {
-            umma_any<BF16, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first | (uint32_t)s);
+            umma_any<P, CTAS>(d_tmem, ((uint64_t)hi << 32) | a_lo, ((uint64_t)hi << 32) | b_lo, idesc, acc_first | (uint32_t)s);
             a_lo += a_step;
             b_lo += b_step;
         }
@@ -278,18 +304,52 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& lo, float& hi) {
     lo = __uint_as_float(u << 16);
     hi = __uint_as_float(u & 0xFFFF0000u);
 }
+// fp16 pair, round-to-nearest-even, saturating to +-65504 instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_fp16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack_fp16(uint32_t u, float& lo, float& hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+    lo = f.x;
+    hi = f.y;
+}
+// two consecutive channels <-> one 32-bit word of a 2-byte-element cell
+template <int P>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (P == PREC_FP16) return pack_fp16(lo, hi);
+    else return pack_bf16(lo, hi);
+}
+template <int P>
+__device__ __forceinline__ void unpack2(uint32_t u, float& lo, float& hi) {
+    if constexpr (P == PREC_FP16) unpack_fp16(u, lo, hi);
+    else unpack_bf16(u, lo, hi);
+}
+// one 16-byte cell <-> its Prec<P>::CW channels
+template <int P>
+__device__ __forceinline__ void cell_to_floats(const uint4& u, float* v) {
+    if constexpr (P == PREC_TF32) {
+        v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+    } else {
+        unpack2<P>(u.x, v[0], v[1]); unpack2<P>(u.y, v[2], v[3]);
+        unpack2<P>(u.z, v[4], v[5]); unpack2<P>(u.w, v[6], v[7]);
+    }
+}
+template <int P>
+__device__ __forceinline__ uint4 floats_to_cell(const float* v) {
+    if constexpr (P == PREC_TF32)
+        return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+    else
+        return make_uint4(pack2<P>(v[0], v[1]), pack2<P>(v[2], v[3]), pack2<P>(v[4], v[5]), pack2<P>(v[6], v[7]));
+}
 
 // 16 consecutive channels of one row <-> 16-byte cells of consecutive chunk planes
-template <bool BF16>
+template <int P>
 __device__ __forceinline__ void store_cells16(uint8_t* p, long long plane_stride, const float (&v)[16]) {
-    if constexpr (BF16) {
+    if constexpr (P != PREC_TF32) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            uint4 u;
-            u.x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]); u.y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-            u.z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]); u.w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(p + g * plane_stride) = u;
-        }
+        for (int g = 0; g < 2; ++g) *reinterpret_cast<uint4*>(p + g * plane_stride) = floats_to_cell<P>(v + g * 8);
     } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -297,17 +357,14 @@ __device__ __forceinline__ void store_cells16(uint8_t* p, long long plane_stride
                 make_float4(v[g * 4 + 0], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
     }
 }
-template <bool BF16>
+template <int P>
 __device__ __forceinline__ void load_cells16(const uint8_t* p, long long plane_stride, float (&v)[16]) {
-    if constexpr (BF16) {
+    if constexpr (P != PREC_TF32) {
         uint4 u[2];
 #pragma unroll
         for (int g = 0; g < 2; ++g) u[g] = *reinterpret_cast<const uint4*>(p + g * plane_stride);
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            unpack_bf16(u[g].x, v[g * 8 + 0], v[g * 8 + 1]); unpack_bf16(u[g].y, v[g * 8 + 2], v[g * 8 + 3]);
-            unpack_bf16(u[g].z, v[g * 8 + 4], v[g * 8 + 5]); unpack_bf16(u[g].w, v[g * 8 + 6], v[g * 8 + 7]);
-        }
+        for (int g = 0; g < 2; ++g) cell_to_floats<P>(u[g], v + g * 8);
     } else {
         float4 u[4];
 #pragma unroll
@@ -337,12 +394,12 @@ __device__ __forceinline__ void add_bias16(float (&v)[16], const float* sb) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <bool BF16>
+template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_kernel(const TcConvArgs a) {
     extern __shared__ __align__(128) uint8_t tc_smem[];
     uint8_t* smem = tc_smem;
-    constexpr int CW = BF16 ? 8 : 4;       // channels per 16-byte cell
+    constexpr int CW = Prec<P>::CW;       // channels per 16-byte cell
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0) HFG_CONV_TL(0);
@@ -442,7 +499,7 @@ tc_conv_kernel(const TcConvArgs a) {
     } else if (warp == 1) {
         // ===================== MMA issuer (one elected lane) =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<BF16>(N);
+        const uint32_t idesc = umma_idesc<P>(N);
         // descriptor high words are loop-invariant; the low word is start>>4 | LBO>>4 << 16,
         // so stepping K chunks / sub-tiles / taps is an add of (bytes >> 4) = rows on the low word
         const uint32_t a_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1 (A and B)
@@ -466,7 +523,7 @@ tc_conv_kernel(const TcConvArgs a) {
                         const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
                         const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil - a.pad - a.min_off);
                         for (int mt = 0; mt < MT; ++mt)
-                            umma_ksteps<BF16>(tmem_base + (uint32_t)(mt * N), a_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                            umma_ksteps<P>(tmem_base + (uint32_t)(mt * N), a_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
                                               2u * (uint32_t)R, 2u * (uint32_t)N, idesc, ksteps, acc_on | (uint32_t)tt);
                     }
                     tc_commit(W_EMPTY(sw_i));
@@ -518,8 +575,8 @@ tc_conv_kernel(const TcConvArgs a) {
                 uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
                 uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
                 if (valid && a.res) {
-                    load_cells16<BF16>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
-                    if (two) load_cells16<BF16>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
+                    load_cells16<P>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
+                    if (two) load_cells16<P>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
                 }
                 if (valid && add_prev) {
                     load_f32x16(ap + (long long)(ch0 / 4) * a.acc_pstride, a.acc_pstride, p0);
@@ -554,7 +611,7 @@ tc_conv_kernel(const TcConvArgs a) {
                     if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                        store_cells16<BF16>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
+                        store_cells16<P>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
                     }
                 }
             }
@@ -572,10 +629,10 @@ tc_conv_kernel(const TcConvArgs a) {
 
 // ------------------------------------------------------------------ small helpers
 // mel [B, C, T] fp32 (reference layout) -> chunk planes in the operand dtype (no activation).
-template <bool BF16>
+template <int P>
 __global__ void tc_pack_input(const float* __restrict__ x, uint8_t* __restrict__ out, int C, int T,
                               long long bstride, long long pstride, int frames_last) {
-    constexpr int CW = BF16 ? 8 : 4;
+    constexpr int CW = Prec<P>::CW;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
@@ -588,34 +645,20 @@ __global__ void tc_pack_input(const float* __restrict__ x, uint8_t* __restrict__
         for (int i = 0; i < CW; ++i) v[i] = x[((size_t)b * C + chunk * CW + i) * T + t];
     }
     uint8_t* p = out + (long long)b * bstride + (long long)chunk * pstride + (long long)(kPadL + t) * 16;
-    if constexpr (BF16) {
-        uint4 u;
-        u.x = pack_bf16(v[0], v[1]); u.y = pack_bf16(v[2], v[3]);
-        u.z = pack_bf16(v[4], v[5]); u.w = pack_bf16(v[6], v[7]);
-        *reinterpret_cast<uint4*>(p) = u;
-    } else {
-        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    }
+    *reinterpret_cast<uint4*>(p) = floats_to_cell<P>(v);
 }
 
 // chunk planes holding leaky_relu(x) -> x as [B, C, T] fp32 (stage dumps for tests).
-template <bool BF16>
+template <int P>
 __global__ void tc_unpack_stage(const uint8_t* __restrict__ in, float* __restrict__ y, int C, int T,
                                 long long bstride, long long pstride, float inv_slope) {
-    constexpr int CW = BF16 ? 8 : 4;
+    constexpr int CW = Prec<P>::CW;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int chunk = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     const uint8_t* p = in + (long long)b * bstride + (long long)chunk * pstride + (long long)(kPadL + t) * 16;
     float v[CW];
-    if constexpr (BF16) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p);
-        unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
-        unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
-    } else {
-        const float4 u = *reinterpret_cast<const float4*>(p);
-        v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
-    }
+    cell_to_floats<P>(*reinterpret_cast<const uint4*>(p), v);
 #pragma unroll
     for (int i = 0; i < CW; ++i)
         y[((size_t)b * C + chunk * CW + i) * T + t] = lrelu_inv(v[i], inv_slope);
@@ -642,42 +685,79 @@ __global__ void tc_zero_pads(const PadJobs jobs) {
     }
 }
 
-// conv_post (C_out = 1, k taps) + tanh from chunk planes that already hold leaky_relu(x)
-// (reference models/hifigan.py:254-256).  One thread per output sample; bandwidth kernel.
-template <bool BF16>
-__global__ void __launch_bounds__(256)
+// conv_post (C_out = 1, K taps) + tanh from chunk planes that already hold leaky_relu(x)
+// (reference models/hifigan.py:254-256).  HBM-bound: reads C channels per step, writes one sample.
+// A block stages (kPostTile + K - 1) rows x C/CW cells in shared memory with coalesced 16-byte loads (each
+// cell is read from global once instead of K times); every thread then produces kPostR consecutive samples
+// from a sliding window: a cell is converted once and feeds up to kPostR * CW FMAs, a chunk's K * CW weights
+// are loaded once per thread.  (The one-sample-per-thread version issued ~700 instructions per sample and
+// ran at 22-26 % of the HBM roofline.)  Accumulation order per sample is chunk -> tap -> channel, as before.
+constexpr int kPostThreads = 128, kPostR = 4, kPostTile = kPostThreads * kPostR, kPostGC = 4;
+template <int P, int K>
+__global__ void __launch_bounds__(kPostThreads)
 tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ y, int C, int T, int k, int pad, long long bstride, long long pstride) {
-    constexpr int CW = BF16 ? 8 : 4;
-    extern __shared__ float wsm[];                          // [k][C]
-    for (int e = threadIdx.x; e < C * k; e += blockDim.x) {
-        const int ci = e / k, j = e - ci * k;
-        wsm[j * C + ci] = w[e];                             // w is [C][k]
+                  float* __restrict__ y, int C, int T, int pad, long long bstride, long long pstride) {
+    constexpr int CW = Prec<P>::CW;
+    constexpr int ROWS = kPostTile + K - 1;
+    extern __shared__ __align__(16) uint8_t post_smem[];
+    const int n_chunks = C / CW;
+    uint4* cells = reinterpret_cast<uint4*>(post_smem);     // [kPostGC][ROWS]: one group of chunk columns at a time
+    float* wsm = reinterpret_cast<float*>(cells + (size_t)kPostGC * ROWS);    // [chunk][K][CW]
+    for (int e = threadIdx.x; e < C * K; e += blockDim.x) {
+        const int ci = e / K, j = e - ci * K;               // w is [C][K]
+        wsm[((ci / CW) * K + j) * CW + (ci % CW)] = w[e];
     }
-    __syncthreads();
     const int b = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    const uint8_t* base = in + (long long)b * bstride + (long long)(kPadL + t - pad) * 16;
-    float acc = 0.f;
-    for (int chunk = 0; chunk < C / CW; ++chunk) {
-        const uint8_t* p = base + (long long)chunk * pstride;
-        for (int j = 0; j < k; ++j) {
-            float v[CW];
-            if constexpr (BF16) {
-                const uint4 u = *reinterpret_cast<const uint4*>(p + j * 16);
-                unpack_bf16(u.x, v[0], v[1]); unpack_bf16(u.y, v[2], v[3]);
-                unpack_bf16(u.z, v[4], v[5]); unpack_bf16(u.w, v[6], v[7]);
-            } else {
-                const float4 u = *reinterpret_cast<const float4*>(p + j * 16);
-                v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
-            }
-            const float* wr = wsm + j * C + chunk * CW;
+    const int t0 = blockIdx.x * kPostTile;
+    // rows t0 - pad .. t0 - pad + ROWS: the planes carry kPadL zero rows in front of the data and the tile
+    // overhang behind it (tc_tp); rows past T + kZeroTail may hold anything but only feed samples >= T
+    const uint8_t* base = in + (long long)b * bstride + (long long)(kPadL + t0 - pad) * 16;
+    const int tl = threadIdx.x * kPostR;                    // first local sample of this thread
+    float acc[kPostR];
 #pragma unroll
-            for (int i = 0; i < CW; ++i) acc = fmaf(wr[i], v[i], acc);
+    for (int i = 0; i < kPostR; ++i) acc[i] = 0.f;
+    for (int c0 = 0; c0 < n_chunks; c0 += kPostGC) {
+        const int gc = (n_chunks - c0) < kPostGC ? (n_chunks - c0) : kPostGC;
+        __syncthreads();                                    // previous group consumed (and wsm written)
+        for (int e = threadIdx.x; e < gc * ROWS; e += blockDim.x) {
+            const int chunk = e / ROWS, r = e - chunk * ROWS;
+            cells[e] = *reinterpret_cast<const uint4*>(base + (long long)(c0 + chunk) * pstride + (long long)r * 16);
+        }
+        __syncthreads();
+        for (int chunk = 0; chunk < gc; ++chunk) {
+            float wv[K][CW];
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+#pragma unroll
+                for (int i = 0; i < CW; i += 4)
+                    *reinterpret_cast<float4*>(&wv[j][i]) =
+                        *reinterpret_cast<const float4*>(wsm + ((c0 + chunk) * K + j) * CW + i);
+            const uint4* col = cells + chunk * ROWS + tl;
+#pragma unroll
+            for (int m = 0; m < kPostR + K - 1; ++m) {      // window row m feeds sample r through tap j = m - r
+                float v[CW];
+                cell_to_floats<P>(col[m], v);
+#pragma unroll
+                for (int r = 0; r < kPostR; ++r) {
+                    const int j = m - r;
+                    if (j >= 0 && j < K) {
+#pragma unroll
+                        for (int i = 0; i < CW; ++i) acc[r] = fmaf(wv[j][i], v[i], acc[r]);
+                    }
+                }
+            }
         }
     }
-    y[(size_t)b * T + t] = tanhf(acc + bias[0]);
+    const float bv = bias[0];
+    const size_t o = (size_t)b * T + t0 + tl;
+    if (t0 + tl + kPostR <= T && (o & 3) == 0) {
+        *reinterpret_cast<float4*>(y + o) =
+            make_float4(tanhf(acc[0] + bv), tanhf(acc[1] + bv), tanhf(acc[2] + bv), tanhf(acc[3] + bv));
+    } else {
+#pragma unroll
+        for (int r = 0; r < kPostR; ++r)
+            if (t0 + tl + r < T) y[o + r] = tanhf(acc[r] + bv);
+    }
 }
 
 }  // namespace hfg

@@ -40,8 +40,12 @@ struct TcPairArgs {
     long long w_half_stride;                              // bytes between the two N-halves (CTA pair only)
     const float* b1; const float* b2;
     uint8_t* out; long long o_bstride, o_pstride;         // leaky_relu(x_new) planes (may be null)
-    float* acc; long long acc_bstride, acc_pstride;       // MRF fp32 partial sums (bytes)
+    float* acc; long long acc_bstride, acc_pstride;       // MRF fp32 partial sums (bytes): unfused-neighbour fallback only
     int acc_mode; float div;
+    // MRF sum without an fp32 round trip (reference :126-131): the last pair of the LAST resblock (TC_ACC_FINAL)
+    // adds the finished outputs of the other resblocks -- ordinary leaky_relu(x_j) planes with the geometry of
+    // `out`, inverted exactly on load -- to its accumulator before conv2, then scales by 1 / n_resblocks.
+    const uint8_t* sum_in[HFG_MAX_STAGES - 1]; int n_sum;
     int N;            // channels (C_in = C_out = N)
     int n_chunks;     // N / CW
     int MT;           // 128-row sub-tiles per tile
@@ -54,18 +58,22 @@ struct TcPairArgs {
     int tap_group;    // taps per W stage
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
-    int dbg;          // timing experiments only (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
+    int dbg;          // HFG_TUNING builds only -- timing experiments (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
     int tiles_per_batch, n_tiles;
     float slope;
     unsigned long long* timeline;   // tuning only (tools/pair_timeline.py): clock64 stamps, [cta < 4][tile < 16][event < 16]
 };
 
-// per-tile phase stamps of the first CTAs (null pointer in production: one predicated-off store per event)
+// per-tile phase stamps of the first CTAs (HFG_TUNING builds only)
+#ifndef HFG_TUNING
+#define HFG_TL(ev, tile_ord) do { } while (0)
+#else
 #define HFG_TL(ev, tile_ord)                                                                                  \
     do {                                                                                                      \
         if (a.timeline && blockIdx.x < 4 && (tile_ord) < 16 && lane == 0)                                     \
             a.timeline[((size_t)blockIdx.x * 16 + (tile_ord)) * 16 + (ev)] = (unsigned long long)clock64();   \
     } while (0)
+#endif
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -84,12 +92,12 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // CTAS = 2: a cluster of two CTAs runs two adjacent tiles in lockstep; the leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256) for both, each CTA stages only its half of every weight tile
 // (half the L2->smem weight traffic and half the B-operand smem reads per SM).
-template <bool BF16, int MINB, int CTAS>
+template <int P, int MINB, int CTAS>
 __global__ void __launch_bounds__(kPairThreads, MINB)
 tc_pair_kernel(const TcPairArgs a) {
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
     uint8_t* smem = tc_pair_smem;
-    constexpr int CW = BF16 ? 8 : 4;
+    constexpr int CW = Prec<P>::CW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, MT = a.MT, R1 = a.R1, RH = a.RH, k = a.k;
@@ -183,8 +191,8 @@ tc_pair_kernel(const TcPairArgs a) {
             if (a_t < n_my && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
                 if (a_kb == 0) HFG_TL(0, a_t);
-                if (leader && (a.dbg & 2)) mbar_arrive(A_FULL(sa_i));
-                if (leader && !(a.dbg & 2)) {
+                if (leader && HFG_DBG(a, 2)) mbar_arrive(A_FULL(sa_i));
+                if (leader && !HFG_DBG(a, 2)) {
                     const uint8_t* ab = tile_src(tile_of(sched0 + a_t * sched_step));
                     mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
                     const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
@@ -202,8 +210,8 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int tap0 = w_g * G;
                 const int g = (k - tap0) < G ? (k - tap0) : G;
                 if (w_conv == 0 && w_kb == 0 && w_g == 0) HFG_TL(11, w_t);
-                if (leader && (a.dbg & 1)) mbar_arrive(W_FULL(sw_i));
-                if (leader && !(a.dbg & 1)) {
+                if (leader && HFG_DBG(a, 1)) mbar_arrive(W_FULL(sw_i));
+                if (leader && !HFG_DBG(a, 1)) {
                     const uint8_t* w = w_conv ? a.w2 : a.w1;
                     mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
@@ -227,7 +235,7 @@ tc_pair_kernel(const TcPairArgs a) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<BF16>(N, 128 * CTAS);
+        const uint32_t idesc = umma_idesc<P>(N, 128 * CTAS);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
         const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)NB) << 16;
         auto commit = [&](uint32_t bar) { if constexpr (CTAS == 2) tc_commit2(bar); else tc_commit(bar); };
@@ -272,11 +280,11 @@ tc_pair_kernel(const TcPairArgs a) {
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int tt = 0; tt < g && !(a.dbg & 16); ++tt) {
+                        for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
-                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * ((a.dbg & 4) ? 8 : a.dil));
+                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : a.dil));
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<BF16, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                umma_ksteps<P, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
                                                         2u * (uint32_t)R1, 2u * (uint32_t)NB, idesc, ksteps,
                                                         acc_on | (uint32_t)tt);
                         }
@@ -307,11 +315,11 @@ tc_pair_kernel(const TcPairArgs a) {
                     tc_fence_after();
                     const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
                     if (leader) {
-                        for (int tt = 0; tt < g && !(a.dbg & 16); ++tt) {
+                        for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
-                            const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * ((a.dbg & 4) ? 8 : 1));
+                            const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : 1));
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<BF16, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                umma_ksteps<P, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
                                                         2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc, ksteps, 1u);
                         }
                         commit(W_EMPTY(sw_i));
@@ -332,7 +340,7 @@ tc_pair_kernel(const TcPairArgs a) {
         const int half = e >> 2;                      // the two warps of a quarter split the sub-tiles ...
         const bool split_cols = MT == 1;              // ... or, with a single sub-tile, alternate column steps
         const int mt_first = split_cols ? 0 : half, mt_step = split_cols ? 1 : 2;
-        const int cs = split_cols ? 2 : 1, ch = split_cols ? half : 0;   // column-step stride / phase
+        const int cs = split_cols ? 2 : 1, ch = split_cols ? half : 0;   // 32-column-step stride / phase
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
@@ -353,7 +361,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 mbar_wait(A_FULL(sa_i), sa_ph);
                 if (kb == 0 && e == 0) HFG_TL(5, it);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
-                for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
+                for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
                     const int lr = mt * 128 + row;                      // output row inside the tile
                     const int t = t0 + lr;
                     const bool add_prev = add_prev_mode && real && lr < a.TO && t < a.T;
@@ -361,18 +369,30 @@ tc_pair_kernel(const TcPairArgs a) {
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
                     const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * KBC * CW);
-                    for (int c16 = 16 * ch; c16 < nck * CW; c16 += 16 * cs) {   // 16 columns at a time
+                    const uint8_t* sump = a.n_sum ? a.sum_in[0] + (long long)b * a.o_bstride + (long long)(kPadL + t) * 16 : nullptr;
+                    for (int c16 = 0; c16 < nck * CW; c16 += 16) {              // 16 columns at a time
                         const int col = kb * KBC * CW + c16;
+                        // column ownership must match epi1 / epi2 (32-column groups alternate between the two
+                        // warps of a lane quarter): this warp's tcgen05.st for tile i+1 may only touch columns
+                        // whose tile-i values it has itself already read in epi2
+                        if (split_cols && ((col >> 5) & 1) != half) continue;
                         float v[16];
-                        load_cells16<BF16>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
+                        load_cells16<P>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
                         float prev[16];
-                        if (add_prev) load_f32x16(accp + (long long)(col / 4) * a.acc_pstride, a.acc_pstride, prev);
+                        if (add_prev && a.n_sum == 0) load_f32x16(accp + (long long)(col / 4) * a.acc_pstride, a.acc_pstride, prev);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = lrelu_inv(v[i], inv_slope);
                         add_bias16(v, sB2 + col);
-                        if (add_prev) {
+                        if (add_prev && a.n_sum == 0) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] += prev[i];
+                        }
+                        if (add_prev && a.n_sum > 0) {                          // + rb_j(x) for the other resblocks
+                            for (int s = 0; s < a.n_sum; ++s) {
+                                load_cells16<P>(sump + (a.sum_in[s] - a.sum_in[0]) + (long long)(col / CW) * a.o_pstride, a.o_pstride, prev);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) v[i] += lrelu_inv(prev[i], inv_slope);
+                            }
                         }
                         tmem_st16(tbase + (uint32_t)c16, v);
                     }
@@ -389,7 +409,7 @@ tc_pair_kernel(const TcPairArgs a) {
             if (e == 0) HFG_TL(7, it);
             // only tiles that touch an utterance edge have H rows outside [0, T) to zero
             const bool edge_tile = (t0 - a.p2 < 0) || (t0 - a.p2 + MT * 128 > a.T);
-            for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
+            for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
                 const bool drop = edge_tile && !(th >= 0 && th < a.T);  // conv2 zero-pads ITS input
@@ -407,14 +427,14 @@ tc_pair_kernel(const TcPairArgs a) {
                     add_bias16(v, sB1 + c0);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
-                    store_cells16<BF16>(hp + (long long)(c0 / CW) * h_plane, h_plane, v);
+                    store_cells16<P>(hp + (long long)(c0 / CW) * h_plane, h_plane, v);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
                         add_bias16(v, sB1 + c0 + 16);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
-                        store_cells16<BF16>(hp + (long long)((c0 + 16) / CW) * h_plane, h_plane, v);
+                        store_cells16<P>(hp + (long long)((c0 + 16) / CW) * h_plane, h_plane, v);
                     }
                 }
             }
@@ -430,7 +450,7 @@ tc_pair_kernel(const TcPairArgs a) {
             mbar_wait(ACC2_FULL, it & 1);
             tc_fence_after();
             if (e == 0) HFG_TL(9, it);
-            for (int mt = mt_first; mt < MT && !(a.dbg & 8); mt += mt_step) {
+            for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
                 const int lr = mt * 128 + row;
                 const int t = t0 + lr;
                 const bool valid = real && lr < a.TO && t < a.T;
@@ -461,7 +481,7 @@ tc_pair_kernel(const TcPairArgs a) {
                             }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                            store_cells16<BF16>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
+                            store_cells16<P>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
                         }
                     }
                 }

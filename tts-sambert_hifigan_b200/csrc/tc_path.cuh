@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "fp32_kernels.cuh"
 #include "model.h"
@@ -13,8 +14,13 @@
 
 namespace hfg {
 
-// Tuning knobs (HFG_TC_*): read from the environment once per thread and cached by literal address,
-// so the launch path does not call getenv() hundreds of times per forward.
+// Tuning knobs (HFG_TC_*).  Production builds compile them out: env_int() is the default, always, so
+// no environment variable can steer kernel selection.  Builds with -DHFG_TUNING (libhfg_b200_tuning.so, used
+// by tools/ and by the kernel-variant tests through HFG_LIB_PATH) read them from the environment once per
+// thread, cached by literal address.
+#ifndef HFG_TUNING
+static inline int env_int(const char*, int dflt) { return dflt; }
+#else
 static inline int env_int(const char* name, int dflt) {
     struct Ent { const char* name; bool set; int val; };
     thread_local Ent cache[48];
@@ -26,6 +32,7 @@ static inline int env_int(const char* name, int dflt) {
     if (n < 48) cache[n++] = e;
     return e.set ? e.val : dflt;
 }
+#endif
 
 // --------------------------------------------------------------------------
 // operand packing
@@ -36,6 +43,23 @@ static inline uint16_t f2bf(float f) {          // round-to-nearest-even
     if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
+}
+static inline uint16_t f2h(float f) {            // fp32 -> fp16, round-to-nearest-even, saturating to +-65504
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+    const uint32_t a = u & 0x7FFFFFFFu;
+    if (a > 0x7F800000u) return (uint16_t)(sign | 0x7E00u);            // NaN
+    if (a >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);           // >= 65520 rounds past the largest finite: saturate
+    if (a < 0x33000001u) return sign;                                  // < 2^-25: rounds to zero
+    int e = (int)(a >> 23) - 127;
+    uint32_t m = (a & 0x7FFFFFu) | 0x800000u;                          // 24-bit significand
+    int shift = e < -14 ? (13 + (-14 - e)) : 13;                       // subnormal halves lose more bits
+    uint32_t q = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (q & 1u))) ++q;
+    uint32_t out = e < -14 ? q : (((uint32_t)(e + 15) << 10) + (q - 0x400u));   // carry into the exponent is correct by construction
+    return (uint16_t)(sign | out);
 }
 static inline float f2tf32(float f) {           // round-to-nearest to 10 mantissa bits
     uint32_t u;
@@ -63,16 +87,16 @@ static inline bool tc_shape_ok(int cin, int cout) { return cin % 16 == 0 && cout
 // Layout: [phase][ntile][kb][tap][chunk(8)][n(N)][cell(CW)], cells of 16 bytes.
 template <typename F>
 static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int phases, int taps_max, F get,
-                            bool pair = false, bool halves = false, int kbc = 8, int only_bf = -1) {
+                            bool pair = false, bool halves = false, int kbc = 8, int only_prec = -1) {
     if (!pair) {
         tp.ok = tc_shape_ok(cin, cout);
         if (!tp.ok) return;
     }
     // halves: two N/2-wide tiles (one per CTA of a pair) in the same [ntile][kb][tap][chunk][n] layout
     const int N = halves ? cout / 2 : (pair ? cout : tc_pick_n(cout)), ntiles = cout / N;
-    for (int bf = 0; bf < 2; ++bf) {
-        if (only_bf >= 0 && bf != only_bf) continue;
-        const int CW = bf ? 8 : 4;
+    for (int prec = 0; prec < 3; ++prec) {
+        if (only_prec >= 0 && prec != only_prec) continue;
+        const int CW = prec == PREC_TF32 ? 4 : 8;
         const int nchunks = cin / CW, nkb = (nchunks + kbc - 1) / kbc;
         // tight layout: [phase][ntile][kb][tap][chunk < nck(kb)][n][cell]
         const size_t per_tile = (size_t)nchunks * N * 16 * taps_max;
@@ -91,12 +115,12 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
                                 for (int e = 0; e < CW; ++e) {
                                     const int ci = (kbc * kb + c) * CW + e;
                                     const float v = get(nt * N + n, ci, ph, tap);
-                                    if (bf) {
-                                        const uint16_t q = f2bf(v);
-                                        memcpy(cell + 2 * e, &q, 2);
-                                    } else {
+                                    if (prec == PREC_TF32) {
                                         const float q = f2tf32(v);
                                         memcpy(cell + 4 * e, &q, 4);
+                                    } else {
+                                        const uint16_t q = prec == PREC_BF16 ? f2bf(v) : f2h(v);
+                                        memcpy(cell + 2 * e, &q, 2);
                                     }
                                 }
                             }
@@ -104,10 +128,10 @@ static void tc_pack_generic(hfg_handle* h, TcPack& tp, int cin, int cout, int ph
                 }
         void* d = h->upload(buf);
         if (pair) {
-            tp.w_pair[bf][halves ? 1 : 0][kbc == 4 ? 1 : 0] = d;
-            if (halves) tp.half_stride[bf][kbc == 4 ? 1 : 0] = (long long)per_tile;
+            tp.w_pair[prec][halves ? 1 : 0][kbc == 4 ? 1 : 0] = d;
+            if (halves) tp.half_stride[prec][kbc == 4 ? 1 : 0] = (long long)per_tile;
         } else {
-            if (bf) tp.w_bf16 = d; else tp.w_tf32 = d;
+            tp.w[prec] = d;
         }
     }
 }
@@ -122,14 +146,13 @@ inline void tc_pack_conv(hfg_handle* h, ConvLayer& L, const HostTensor& w, const
     // packs of the fused ResBlock kernel: whole-N (one CTA) and N-halves (cta_group::2 pair), K blocks of
     // 8 cells; tf32 additionally with K blocks of 4 cells (the fp32 H tile leaves less room for A stages)
     const bool can_halve = L.cout % 32 == 0;
-    L.tc.w_pair[1][0][0] = L.tc.w_bf16;
-    L.tc.w_pair[0][0][0] = L.tc.w_tf32;
+    for (int prec = 0; prec < 3; ++prec) L.tc.w_pair[prec][0][0] = L.tc.w[prec];
     if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 8);
     // K blocks of 4 cells let tf32 C=128 run MT=2 tiles, but measured slower than MT=1 with K blocks of 8
     // (profiles/r1_tuning.md): packed only on request (HFG_TC_PACK_KBC4=1, tuning experiments)
     if (L.cin / 4 >= 16 && env_int("HFG_TC_PACK_KBC4", 0)) {
-        tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, false, 4, /*only tf32*/ 0);
-        if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 4, 0);
+        tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, false, 4, /*only tf32*/ PREC_TF32);
+        if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 4, PREC_TF32);
     }
 }
 inline void tc_pack_up(hfg_handle* h, UpLayer& L, const HostTensor& w, const HostTensor&) {
@@ -187,16 +210,38 @@ static inline TcPlane tc_plane(int B, int C, long long T, int cw, size_t& cursor
     return p;
 }
 
+static inline int tc_prec_of_mode(int mode) {
+    return mode == HFG_MODE_BF16 ? PREC_BF16 : (mode == HFG_MODE_FP16 ? PREC_FP16 : PREC_TF32);
+}
+static inline bool tc_is_tc_mode(int mode) { return mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16 || mode == HFG_MODE_FP16; }
+
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; };
+static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, int prec);
+
+// How the MRF sum (reference models/hifigan.py:126-131) of stage i is formed.
+//   sum planes (default): every resblock but the last writes its output like any other pair; the last pair of the
+//     LAST resblock adds those planes in its pre2 phase.  No fp32 accumulator plane exists.
+//   fp32 ACC plane (WRITE -> ADD -> FINAL): only when that last pair does not fit the fused kernel and runs as
+//     two plain convolutions.
+static inline bool tc_stage_sum_planes(const hfg_handle* h, size_t i, int n_chunks, int prec) {
+    const auto& mrf = h->mrfs[i];
+    if (mrf.size() < 2) return false;                       // a single resblock has nothing to sum
+    if ((int)mrf.size() - 1 > HFG_MAX_STAGES - 1 || !env_int("HFG_TC_SUM_PLANES", 1)) return false;
+    return tc_pair_geometry(h, mrf.back().back(), n_chunks, prec).ok;
+}
+
 struct TcPlan {
     TcPlane mel, pre;                       // packed mel, conv_pre output
-    // per stage: X = upsampler output, Y = MRF output, ACC = fp32 running sum over the resblocks, and per
-    // resblock (they run concurrently) two ping-pong planes R, H plus a scratch S for the unfused fallback
-    struct Stage { TcPlane X, Y, ACC; struct { TcPlane R, H, S; } rb[HFG_MAX_STAGES]; } st[HFG_MAX_STAGES];
+    // per stage: X = upsampler output, Y = MRF output and, per resblock (they run concurrently), two ping-pong
+    // planes R, H.  Only where a pair does not fit the fused kernel: a scratch S for its intermediate, and an
+    // fp32 running-sum plane ACC if that pair is the one that forms the MRF sum.
+    struct Stage { TcPlane X, Y, ACC; bool sum_planes = false; struct { TcPlane R, H, S; bool fused = true; } rb[HFG_MAX_STAGES]; } st[HFG_MAX_STAGES];
     size_t total = 0;
 };
 
 static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
-    const int cw = mode == HFG_MODE_BF16 ? 8 : 4;
+    const int prec = tc_prec_of_mode(mode);
+    const int cw = prec == PREC_TF32 ? 4 : 8;
     TcPlan p;
     size_t cur = 0;
     p.mel = tc_plane(B, h->cfg.n_mels, T, cw, cur);
@@ -205,14 +250,24 @@ static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
     for (size_t i = 0; i < h->ups.size(); ++i) {
         const UpLayer& U = h->ups[i];
         t = (t - 1) * U.u - 2 * U.p + U.k;
-        p.st[i].X = tc_plane(B, U.cout, t, cw, cur);
-        p.st[i].Y = tc_plane(B, U.cout, t, cw, cur);
-        for (int j = 0; j < h->cfg.num_resblocks; ++j) {
-            p.st[i].rb[j].R = tc_plane(B, U.cout, t, cw, cur);
-            p.st[i].rb[j].H = tc_plane(B, U.cout, t, cw, cur);
-            p.st[i].rb[j].S = tc_plane(B, U.cout, t, cw, cur);
+        auto& S = p.st[i];
+        S.X = tc_plane(B, U.cout, t, cw, cur);
+        S.Y = tc_plane(B, U.cout, t, cw, cur);
+        const int n_rb = h->cfg.num_resblocks;
+        S.sum_planes = tc_stage_sum_planes(h, i, S.X.nchunks, prec);
+        for (int j = 0; j < n_rb; ++j) {
+            const auto& rb = h->mrfs[i][j];
+            bool fused = true;
+            for (auto& P : rb) fused = fused && tc_pair_geometry(h, P, S.X.nchunks, prec).ok;
+            S.rb[j].fused = fused;
+            // R: output of pair 0 (or, with sum planes, the finished output of a one-pair resblock); H: its partner
+            const bool need_r = rb.size() > 1 || (S.sum_planes && j + 1 < n_rb);
+            const bool need_h = rb.size() > 2 || (S.sum_planes && j + 1 < n_rb && rb.size() > 1);
+            if (need_r) S.rb[j].R = tc_plane(B, U.cout, t, cw, cur);
+            if (need_h) S.rb[j].H = tc_plane(B, U.cout, t, cw, cur);
+            if (!fused) S.rb[j].S = tc_plane(B, U.cout, t, cw, cur);
         }
-        p.st[i].ACC = tc_plane(B, U.cout, t, 4, cur);          // fp32 accumulator cells
+        if (!S.sum_planes && n_rb > 1) S.ACC = tc_plane(B, U.cout, t, 4, cur);          // fp32 accumulator cells
     }
     p.total = cur;
     return p;
@@ -238,7 +293,7 @@ static inline int tc_tap_group(int N, int nck_max, int taps) {
     return std::min(g, taps);
 }
 
-template <bool BF16>
+template <int P>
 static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, int cout, const char* label,
                            double flops, double bytes) {
     const int nck_max = std::min(8, a.a_nchunks);
@@ -284,7 +339,7 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     // 8 epilogue warps when the CTA owns its SM anyway (big tiles: latency-bound epilogue, profiles/r1_tuning.md);
     // 4 when two CTAs can share the SM (narrow layers), which hides the epilogue better than more warps
     const int threads = (2 * (smem + 1024) <= 227 * 1024 && env_int("HFG_TC_CONV_WARPS", 0) != 8) ? 192 : kTcThreads;
-    tc_conv_kernel<BF16><<<grid, threads, smem, st>>>(a);
+    tc_conv_kernel<P><<<grid, threads, smem, st>>>(a);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_conv_kernel launch");
     if (tl_dev) {
@@ -305,11 +360,10 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
 }
 
 // ---- fused ResBlock pair ----
-struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; };
 
 // Persistent, double-buffered launch of a plain-epilogue convolution (conv_pre, upsamplers): tc_up_kernel.
 // Returns false when the geometry does not fit (the caller falls back to tc_launch_conv).
-template <bool BF16>
+template <int P>
 static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, int cout, const char* label,
                          double flops, double bytes) {
     if (!env_int("HFG_TC_UP_PERSIST", 1)) return false;
@@ -368,13 +422,14 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
         fprintf(stderr, "[up] %s N=%d MT=%d G=%d sa=%d sw=%d smem=%zu grid=%d items=%d\n", label, a.N, MT, G, sa, sw, smem,
                 grid, ua.n_items);
     h->prof_begin(st, label, flops, bytes);
-    tc_up_kernel<BF16><<<grid, kTcThreads, smem, st>>>(ua);
+    tc_up_kernel<P><<<grid, kTcThreads, smem, st>>>(ua);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_up_kernel launch");
     return true;
 }
 
-static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
+static inline int tc_pair_ctas(const PairLayers& P, int prec) {
+    const bool bf16 = prec != PREC_TF32;                               // 2-byte operands (bf16 or fp16)
     // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
     // (profiles/r1_tuning.md sections 5 and 7): every C >= 64 layer, except tf32 C = 256 whose fp32 H tile
     // leaves too little shared memory (the fused pair measured slower than two unfused launches there).
@@ -382,10 +437,10 @@ static inline int tc_pair_ctas(const PairLayers& P, bool bf16) {
     const int N = P.c1.cout;
     const int dflt = (N >= 64 && (bf16 || N <= 128)) ? 2 : 1;
     const int want = env_int("HFG_TC_PAIR_CTAS", dflt);
-    return (want == 2 && P.c1.tc.w_pair[bf16 ? 1 : 0][1][0] && P.c2.tc.w_pair[bf16 ? 1 : 0][1][0]) ? 2 : 1;
+    return (want == 2 && P.c1.tc.w_pair[prec][1][0] && P.c2.tc.w_pair[prec][1][0]) ? 2 : 1;
 }
 
-static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, bool bf16) {
+static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, int prec) {
     PairGeom g{};
     const int N = P.c1.cout, k = P.c1.k, p1 = P.c1.pad, p2 = P.c2.pad;
     g.ok = false;
@@ -393,7 +448,7 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     if (N > env_int("HFG_TC_FUSE_MAXC", 256) || N % 16 != 0 || P.c1.cin != N || P.c2.cin != N || P.c2.cout != N) return g;
     if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
     const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
-    const int ctas = tc_pair_ctas(P, bf16);
+    const int ctas = tc_pair_ctas(P, prec);
     const int NB = N / ctas;                                              // weight rows staged per CTA
     // Candidates from the largest tile down.  Measured rule (profiles/r1_tuning.md): two co-resident
     // CTAs per SM beat one CTA with a larger tile (one CTA's epilogue hides behind the other's MMAs),
@@ -404,7 +459,7 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     for (int MT : {4, 2, 1}) {
         if (MT > mt_cap || 2 * MT * N > 512) continue;
       for (int kbc : {8, 4}) {
-        if (!P.c1.tc.w_pair[bf16 ? 1 : 0][ctas - 1][kbc == 4 ? 1 : 0]) continue;
+        if (!P.c1.tc.w_pair[prec][ctas - 1][kbc == 4 ? 1 : 0]) continue;
         if (kbc == 4 && env_int("HFG_TC_PAIR_NO_KBC4", 0)) continue;
         const int nck_max = std::min(kbc, n_chunks), n_kb = (n_chunks + kbc - 1) / kbc;
         // W ring.  Measured (profiles/r1_tuning.md section 6): with the data always ready the kernel is still
@@ -470,43 +525,44 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     return best;
 }
 
-template <bool BF16>
-static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, const PairGeom& g,
+template <int P>
+static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, const PairGeom& g,
                            const uint8_t* in, long long in_b, long long in_p, int n_chunks,
                            uint8_t* out, long long out_b, long long out_p,
                            float* acc, long long acc_b, long long acc_p, int acc_mode, float div,
+                           const uint8_t* const* sum_in, int n_sum,
                            int B, int T, const char* label) {
-    constexpr int ESZ = BF16 ? 2 : 4;
+    constexpr int ESZ = Prec<P>::ESZ;
     TcPairArgs a{};
     a.a = in; a.a_bstride = in_b; a.a_pstride = in_p;
-    const int vb = BF16 ? 1 : 0, vk = g.kbc == 4 ? 1 : 0;
-    a.w1 = reinterpret_cast<const uint8_t*>(P.c1.tc.w_pair[vb][g.ctas - 1][vk]);
-    a.w2 = reinterpret_cast<const uint8_t*>(P.c2.tc.w_pair[vb][g.ctas - 1][vk]);
-    a.w_half_stride = P.c1.tc.half_stride[vb][vk];
+    const int vk = g.kbc == 4 ? 1 : 0;
+    a.w1 = reinterpret_cast<const uint8_t*>(L.c1.tc.w_pair[P][g.ctas - 1][vk]);
+    a.w2 = reinterpret_cast<const uint8_t*>(L.c2.tc.w_pair[P][g.ctas - 1][vk]);
+    a.w_half_stride = L.c1.tc.half_stride[P][vk];
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.dbg = env_int("HFG_TC_DBG", 0);
-    a.b1 = P.c1.bias; a.b2 = P.c2.bias;
+    a.b1 = L.c1.bias; a.b2 = L.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
-    a.N = P.c1.cout; a.n_chunks = n_chunks; a.MT = g.MT; a.T = T;
-    a.k = P.c1.k; a.dil = P.c1.dil; a.p1 = P.c1.pad; a.p2 = P.c2.pad;
+    a.n_sum = n_sum;
+    for (int s = 0; s < n_sum; ++s) a.sum_in[s] = sum_in[s];
+    a.N = L.c1.cout; a.n_chunks = n_chunks; a.MT = g.MT; a.T = T;
+    a.k = L.c1.k; a.dil = L.c1.dil; a.p1 = L.c1.pad; a.p2 = L.c2.pad;
     a.R1 = g.R1; a.RH = g.RH; a.TO = g.TO; a.sa = g.sa; a.sw = g.sw; a.tap_group = g.G;
     a.tiles_per_batch = (T + g.TO - 1) / g.TO;
     a.n_tiles = a.tiles_per_batch * B;
     a.slope = 0.1f;
     a.timeline = h->pair_timeline;
     // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
-    // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
     const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
     const int ctas = g.ctas;
     using KernelFn = void (*)(TcPairArgs);
     KernelFn fn = nullptr;
-    if (ctas == 2) fn = two ? tc_pair_kernel<BF16, 2, 2> : tc_pair_kernel<BF16, 1, 2>;
-    else fn = two ? tc_pair_kernel<BF16, 2, 1> : tc_pair_kernel<BF16, 1, 1>;
+    if (ctas == 2) fn = two ? tc_pair_kernel<P, 2, 2> : tc_pair_kernel<P, 1, 2>;
+    else fn = two ? tc_pair_kernel<P, 2, 1> : tc_pair_kernel<P, 1, 1>;
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
-    static int regs_cache[2][2][2] = {};
-    int& regs = regs_cache[BF16 ? 1 : 0][two ? 1 : 0][ctas - 1];
+    int& regs = h->pair_regs[P][two ? 1 : 0][ctas - 1];
     if (regs == 0) {
         cudaFuncAttributes fa{};
         check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
@@ -518,7 +574,8 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     const int grid = ctas * std::min(n_sched, (h->sm_count / ctas) * occ);
     const double C = a.N;
     const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
-    const double bytes = (double)B * T * C * ESZ * (out ? 2 : 1) +
+    // algorithmic bytes: the activation in and out once, the other resblocks' outputs (or the fp32 running sum), the weights
+    const double bytes = (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
                          (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     if (env_int("HFG_TC_VERBOSE", 0))
         fprintf(stderr, "[pair] N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d\n",
@@ -539,12 +596,11 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& P, 
     check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
 }
 
-template <bool BF16>
+template <int P>
 static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws,
                             cudaStream_t st, float* const* stage_out) {
-    constexpr int CW = BF16 ? 8 : 4;
-    constexpr int ESZ = BF16 ? 2 : 4;
-    const TcPlan plan = tc_plan(h, B, T, BF16 ? HFG_MODE_BF16 : HFG_MODE_TF32);
+    constexpr int ESZ = Prec<P>::ESZ;
+    const TcPlan plan = tc_plan(h, B, T, P == PREC_BF16 ? HFG_MODE_BF16 : (P == PREC_FP16 ? HFG_MODE_FP16 : HFG_MODE_TF32));
     const float slope = 0.1f;
     const int n_rb = h->cfg.num_resblocks;
     auto ptr = [&](const TcPlane& p) { return reinterpret_cast<uint8_t*>(ws + p.off); };
@@ -565,16 +621,16 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             jobs.job[jobs.n++] = PadJob{ptr(p), (long long)B * p.nchunks, p.TP, p.T};
             if (jobs.n == 40) flush();
         };
-        // which planes are ever read: R/H only with more than one pair per resblock, S only without the fused kernel
+        // which planes are ever read through a convolution's halo: R/H only with more than one pair per resblock
+        // (a finished resblock output that only feeds the MRF sum is read at valid rows only), S only without
+        // the fused kernel
         add(plan.mel); add(plan.pre);
         for (size_t i = 0; i < h->ups.size(); ++i) {
             add(plan.st[i].X); add(plan.st[i].Y);
             for (int j = 0; j < n_rb; ++j) {
-                bool fused = true;
-                for (auto& P : h->mrfs[i][j]) fused = fused && tc_pair_geometry(h, P, plan.st[i].X.nchunks, BF16).ok;
                 if (h->mrfs[i][j].size() > 1) add(plan.st[i].rb[j].R);
                 if (h->mrfs[i][j].size() > 2) add(plan.st[i].rb[j].H);
-                if (!fused) add(plan.st[i].rb[j].S);
+                if (!plan.st[i].rb[j].fused) add(plan.st[i].rb[j].S);
             }
         }
         flush();
@@ -583,7 +639,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     {
         dim3 grid((T + 127) / 128, plan.mel.nchunks, B);
         h->prof_begin(st, "pack_mel", 0, (double)B * h->cfg.n_mels * T * (4 + ESZ));
-        tc_pack_input<BF16><<<grid, 128, 0, st>>>(mel, ptr(plan.mel), h->cfg.n_mels, T, plan.mel.bstride, plan.mel.pstride,
+        tc_pack_input<P><<<grid, 128, 0, st>>>(mel, ptr(plan.mel), h->cfg.n_mels, T, plan.mel.bstride, plan.mel.pstride,
                                                   h->mel_layout);
         h->prof_end(st);
         check_cuda(cudaGetLastError(), "tc_pack_input launch");
@@ -591,7 +647,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     auto dump = [&](int idx, const TcPlane& p) {
         if (!stage_out || !stage_out[idx]) return;
         dim3 grid((p.T + 127) / 128, p.nchunks, B);
-        tc_unpack_stage<BF16><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
+        tc_unpack_stage<P><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
         check_cuda(cudaGetLastError(), "tc_unpack_stage launch");
     };
     auto conv = [&](cudaStream_t st, const ConvLayer& L, const TcPlane& in, const TcPlane* out, const TcPlane* res,
@@ -599,7 +655,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         TcConvArgs a{};
         a.a = ptr(in); a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
         a.N = tc_pick_n(L.cout);
-        a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
+        a.w = reinterpret_cast<const uint8_t*>(L.tc.w[P]);
         a.w_ntile_stride = (long long)in.nchunks * L.k * a.N * 16;
         a.w_phase_stride = 0;
         a.bias = L.bias;
@@ -617,8 +673,8 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         const double bytes = (double)B * in.T * ESZ * (L.cin + L.cout * (res ? 2 : 1)) +
                              (acc ? 4.0 * B * in.T * L.cout * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) +
                              (double)ESZ * L.cin * L.cout * L.k;
-        if (!tc_launch_up<BF16>(h, st, a, B, L.cout, label, flops, bytes))
-            tc_launch_conv<BF16>(h, st, a, B, L.cout, label, flops, bytes);
+        if (!tc_launch_up<P>(h, st, a, B, L.cout, label, flops, bytes))
+            tc_launch_conv<P>(h, st, a, B, L.cout, label, flops, bytes);
     };
 
     // conv_pre (reference :238); its output is stored as leaky_relu(x) for ups[0] (:244)
@@ -640,8 +696,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             const bool stack = U.tc_stack.ok && env_int("HFG_TC_UPS_STACK", U.u * U.cout <= 128 ? 1 : 0);
             const int cout_v = stack ? U.u * U.cout : U.cout;          // (virtual) output channels of the GEMM
             a.N = tc_pick_n(cout_v);
-            a.w = reinterpret_cast<const uint8_t*>(stack ? (BF16 ? U.tc_stack.w_bf16 : U.tc_stack.w_tf32)
-                                                         : (BF16 ? U.tc.w_bf16 : U.tc.w_tf32));
+            a.w = reinterpret_cast<const uint8_t*>(stack ? U.tc_stack.w[P] : U.tc.w[P]);
             a.w_ntile_stride = (long long)cur->nchunks * U.taps_max * a.N * 16;
             a.w_phase_stride = stack ? 0 : a.w_ntile_stride * (U.cout / a.N);
             a.stack_cout = stack ? U.cout : 0;
@@ -657,8 +712,8 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             const double bytes = (double)B * ESZ * ((double)U.cin * cur->T + (double)U.cout * S.X.T) +
                                  (double)ESZ * U.cin * U.cout * U.k;
             const std::string ulab = "ups" + std::to_string(i);
-            if (!tc_launch_up<BF16>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes))
-                tc_launch_conv<BF16>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes);
+            if (!tc_launch_up<P>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes))
+                tc_launch_conv<P>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes);
         }
         h->stage_end(st);
         dump(1 + 2 * (int)i, S.X);
@@ -678,7 +733,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         // kernels fill the gaps of the MMA-bound long ones.
         std::vector<int> order(n_rb), slot(n_rb, 0);
         for (int j = 0; j < n_rb; ++j) order[j] = j;
-        auto cost = [&](int j) { int c = 0; for (auto& P : h->mrfs[i][j]) c += P.c1.k + P.c2.k; return c; };
+        auto cost = [&](int j) { int c = 0; for (auto& pl : h->mrfs[i][j]) c += pl.c1.k + pl.c2.k; return c; };
         if (n_streams > 1 && env_int("HFG_TC_STREAM_LPT", 0))
             std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost(x) > cost(y); });
         for (int r = 0; r < n_rb; ++r) slot[order[r]] = (n_streams - 1 - (r % n_streams));   // rank 0 -> last side stream
@@ -689,10 +744,14 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             for (int s = 1; s < n_streams; ++s)
                 check_cuda(cudaStreamWaitEvent(h->side[s - 1], h->ev_fork, 0), "cudaStreamWaitEvent(fork)");
         }
-        // pass 0: every pair but the last, costliest resblock first; pass 1: the last pairs in resblock order,
-        // because the running sum is updated in that order (WRITE, ADD ..., FINAL) and an event has to be
-        // recorded before the wait on it is enqueued
+        // pass 0: every pair but the last, costliest resblock first; pass 1: the last pairs in resblock order --
+        // the pair that forms the MRF sum comes last and an event has to be recorded before the wait on it is
+        // enqueued.  With sum planes (tc_stage_sum_planes) the last pairs of resblocks 0 .. n-2 are ordinary
+        // pairs whose outputs the last pair of resblock n-1 adds up; otherwise the fp32 ACC plane is updated
+        // WRITE -> ADD ... -> FINAL.
+        const bool sum_planes = S.sum_planes;
         std::vector<const TcPlane*> src(n_rb, &S.X);
+        std::vector<const uint8_t*> fin;                   // finished outputs of resblocks 0 .. n-2 (sum planes)
         for (int pass = 0; pass < 2; ++pass) {
             for (int q = 0; q < n_rb; ++q) {
                 const int j = pass == 0 ? order[q] : q;
@@ -704,24 +763,41 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                 for (size_t l = l_begin; l < l_end; ++l) {
                     const TcPlane* r = src[j];
                     const bool last = (l + 1 == rb.size());
+                    const bool closes = last && j == n_rb - 1;          // this pair forms the MRF output
                     int mode = TC_ACC_NONE;
-                    if (last && n_rb > 1) mode = j == 0 ? TC_ACC_WRITE : (j == n_rb - 1 ? TC_ACC_FINAL : TC_ACC_ADD);
-                    if (last && j > 0 && n_streams > 1 && stream_of(j - 1) != sj)
-                        check_cuda(cudaStreamWaitEvent(sj, h->ev_sum[j - 1], 0), "cudaStreamWaitEvent(sum)");
-                    // destination of this pair: ping-pong between R and H; the last pair feeds the MRF sum / Y
-                    const TcPlane* dst = last ? ((mode == TC_ACC_WRITE || mode == TC_ACC_ADD) ? nullptr : &S.Y)
-                                              : (r == &W.R ? &W.H : &W.R);
-                    const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, BF16);
+                    if (last && n_rb > 1) {
+                        if (sum_planes) mode = closes ? TC_ACC_FINAL : TC_ACC_NONE;
+                        else mode = j == 0 ? TC_ACC_WRITE : (closes ? TC_ACC_FINAL : TC_ACC_ADD);
+                    }
+                    if (last && n_streams > 1) {
+                        if (sum_planes && closes) {
+                            for (int jj = 0; jj + 1 < n_rb; ++jj)
+                                if (stream_of(jj) != sj)
+                                    check_cuda(cudaStreamWaitEvent(sj, h->ev_sum[jj], 0), "cudaStreamWaitEvent(sum)");
+                        } else if (!sum_planes && j > 0 && stream_of(j - 1) != sj) {
+                            check_cuda(cudaStreamWaitEvent(sj, h->ev_sum[j - 1], 0), "cudaStreamWaitEvent(sum)");
+                        }
+                    }
+                    // destination of this pair: ping-pong between R and H; the closing pair writes Y; with the
+                    // ACC plane the other last pairs write nothing but the running sum
+                    const TcPlane* dst = (r == &W.R ? &W.H : &W.R);
+                    if (closes || (last && n_rb == 1)) dst = &S.Y;
+                    else if (last && !sum_planes) dst = nullptr;
+                    const bool use_acc = mode != TC_ACC_NONE && !sum_planes;
+                    const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, P);
                     if (g.ok) {
-                        tc_launch_pair<BF16>(h, sj, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
-                                             dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
-                                             mode != TC_ACC_NONE ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
-                                             S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb, B, S.X.T, lab.c_str());
+                        tc_launch_pair<P>(h, sj, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
+                                          dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
+                                          use_acc ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
+                                          S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb,
+                                          (sum_planes && closes) ? fin.data() : nullptr, (sum_planes && closes) ? (int)fin.size() : 0,
+                                          B, S.X.T, lab.c_str());
                     } else {
                         // unfused fallback: conv1 -> scratch, conv2 (+ residual) -> dst
                         conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
-                        conv(sj, rb[l].c2, W.S, dst, r, mode != TC_ACC_NONE ? &S.ACC : nullptr, mode, lab.c_str());
+                        conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, lab.c_str());
                     }
+                    if (last && sum_planes && !closes) fin.push_back(ptr(*dst));
                     if (last && n_streams > 1 && j + 1 < n_rb)
                         check_cuda(cudaEventRecord(h->ev_sum[j], sj), "cudaEventRecord(sum)");
                     if (!last) src[j] = dst;
@@ -742,28 +818,27 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     // wav = tanh(conv_post(leaky_relu(x)))  (reference :254-256); planes already hold leaky_relu(x)
     {
         const int Tw = cur->T;
-        dim3 grid((Tw + 255) / 256, B);
+        dim3 grid((Tw + kPostTile - 1) / kPostTile, B);
+        const size_t post_smem = (size_t)kPostGC * (kPostTile + 6) * 16 + sizeof(float) * h->post_cin * 7;
         h->stage_begin(st, "tail");
         h->prof_begin(st, "conv_post", 2.0 * h->post_cin * 7 * (double)B * Tw,
                       (double)B * Tw * (ESZ * h->post_cin + 4.0));
-        tc_conv_post_tanh<BF16><<<grid, 256, sizeof(float) * h->post_cin * 7, st>>>(
-            ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 7, 3, cur->bstride, cur->pstride);
+        tc_conv_post_tanh<P, 7><<<grid, kPostThreads, post_smem, st>>>(
+            ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride);
         h->prof_end(st);
         h->stage_end(st);
         check_cuda(cudaGetLastError(), "tc_conv_post_tanh launch");
     }
-    (void)CW;
 }
 
 // Micro-benchmark of ONE MRF convolution launch on scratch planes (tuning / ncu).
 // which: 0 = convs1[pair], 1 = convs2[pair] (with residual).  Returns avg ms per launch.
-template <bool BF16>
+template <int P>
 static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pair, int which, int B, int T, int iters) {
-    constexpr int ESZ = BF16 ? 2 : 4;
-    const PairLayers& P = h->mrfs.at(stage).at(resblock).at(pair);
-    const ConvLayer& L = which == 1 ? P.c2 : P.c1;
+    const PairLayers& PL = h->mrfs.at(stage).at(resblock).at(pair);
+    const ConvLayer& L = which == 1 ? PL.c2 : PL.c1;
     size_t cur = 0;
-    const int cw = BF16 ? 8 : 4;
+    const int cw = Prec<P>::CW;
     TcPlane in = tc_plane(B, L.cin, T, cw, cur), out = tc_plane(B, L.cout, T, cw, cur), res = tc_plane(B, L.cout, T, cw, cur);
     char* ws = nullptr;
     check_cuda(cudaMalloc((void**)&ws, cur), "cudaMalloc(bench)");
@@ -772,7 +847,7 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     TcConvArgs a{};
     a.a = (uint8_t*)ws + in.off; a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
     a.N = tc_pick_n(L.cout);
-    a.w = reinterpret_cast<const uint8_t*>(BF16 ? L.tc.w_bf16 : L.tc.w_tf32);
+    a.w = reinterpret_cast<const uint8_t*>(L.tc.w[P]);
     a.w_ntile_stride = (long long)in.nchunks * L.k * a.N * 16;
     a.bias = L.bias;
     a.out = (uint8_t*)ws + out.off; a.res = which ? (uint8_t*)ws + res.off : nullptr;
@@ -784,15 +859,15 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     h->profiling = 0;
     cudaEvent_t e0, e1;
     check_cuda(cudaEventCreate(&e0), "event"); check_cuda(cudaEventCreate(&e1), "event");
-    const PairGeom g = tc_pair_geometry(h, P, in.nchunks, BF16);
+    const PairGeom g = tc_pair_geometry(h, PL, in.nchunks, P);
     if (which == 2 && !g.ok) throw StatusError(HFG_ERR_UNSUPPORTED, "fused pair does not fit for this layer");
     auto launch = [&]() {
         if (which == 2)
-            tc_launch_pair<BF16>(h, st, P, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
-                                 (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
-                                 B, T, "bench");
+            tc_launch_pair<P>(h, st, PL, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
+                              (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
+                              nullptr, 0, B, T, "bench");
         else
-            tc_launch_conv<BF16>(h, st, a, B, L.cout, "bench", 0, 0);
+            tc_launch_conv<P>(h, st, a, B, L.cout, "bench", 0, 0);
     };
     for (int i = 0; i < 3; ++i) launch();
     if (const char* tl_path = getenv("HFG_TC_TIMELINE")) {
@@ -809,7 +884,7 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
         cudaFree(d);
         if (FILE* f = fopen(tl_path, "a")) {
             fprintf(f, "# stage=%d resblock=%d pair=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d ctas=%d\n", stage, resblock, pair,
-                    L.cout, L.k, P.c1.dil, g.MT, g.G, g.sa, g.sw, g.ctas);
+                    L.cout, L.k, PL.c1.dil, g.MT, g.G, g.sa, g.sw, g.ctas);
             for (size_t i = 0; i < n; i += 16) {
                 for (int e = 0; e < 16; ++e) fprintf(f, "%llu ", hbuf[i + e]);
                 fprintf(f, "\n");
@@ -826,7 +901,6 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(ws);
     h->profiling = was;
-    (void)ESZ;
     return ms / iters;
 }
 
@@ -834,8 +908,9 @@ inline void tc_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
                        cudaStream_t st, float* const* stage_out) {
     if (h->cc_major != 10)
         throw StatusError(HFG_ERR_UNSUPPORTED, "tensor-core modes need an sm_100 device (tcgen05)");
-    if (mode == HFG_MODE_BF16) tc_forward_impl<true>(h, mel, B, T, wav, ws, st, stage_out);
-    else tc_forward_impl<false>(h, mel, B, T, wav, ws, st, stage_out);
+    if (mode == HFG_MODE_BF16) tc_forward_impl<PREC_BF16>(h, mel, B, T, wav, ws, st, stage_out);
+    else if (mode == HFG_MODE_FP16) tc_forward_impl<PREC_FP16>(h, mel, B, T, wav, ws, st, stage_out);
+    else tc_forward_impl<PREC_TF32>(h, mel, B, T, wav, ws, st, stage_out);
 }
 
 inline void configure_kernels(hfg_handle*) {
@@ -843,16 +918,18 @@ inline void configure_kernels(hfg_handle*) {
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
     check_cuda(cudaFuncSetAttribute(conv_tile_fp32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
-    check_cuda(cudaFuncSetAttribute(tc_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     auto big = [](auto fn) {
         check_cuda(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "attr");
     };
-    big(tc_up_kernel<true>); big(tc_up_kernel<false>);
-    big(tc_pair_kernel<true, 1, 1>); big(tc_pair_kernel<false, 1, 1>);
-    big(tc_pair_kernel<true, 2, 1>); big(tc_pair_kernel<false, 2, 1>);
-    big(tc_pair_kernel<true, 1, 2>); big(tc_pair_kernel<false, 1, 2>);
-    big(tc_pair_kernel<true, 2, 2>); big(tc_pair_kernel<false, 2, 2>);
+    auto each = [&](auto prec) {
+        constexpr int P = decltype(prec)::value;
+        big(tc_conv_kernel<P>); big(tc_up_kernel<P>);
+        big(tc_pair_kernel<P, 1, 1>); big(tc_pair_kernel<P, 2, 1>);
+        big(tc_pair_kernel<P, 1, 2>); big(tc_pair_kernel<P, 2, 2>);
+    };
+    each(std::integral_constant<int, PREC_TF32>{});
+    each(std::integral_constant<int, PREC_BF16>{});
+    each(std::integral_constant<int, PREC_FP16>{});
 }
 
 }  // namespace hfg

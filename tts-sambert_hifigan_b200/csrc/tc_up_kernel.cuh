@@ -25,13 +25,13 @@ struct TcUpArgs {
     int cout_total;      // bias entries staged in shared memory (virtual channels when phases are stacked)
 };
 
-template <bool BF16>
+template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_up_kernel(const TcUpArgs ua) {
     const TcConvArgs& a = ua.c;
     extern __shared__ __align__(128) uint8_t tc_up_smem[];
     uint8_t* smem = tc_up_smem;
-    constexpr int CW = BF16 ? 8 : 4;
+    constexpr int CW = Prec<P>::CW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, MT = a.MT, R = a.R;
@@ -140,7 +140,7 @@ tc_up_kernel(const TcUpArgs ua) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<BF16>(N);
+        const uint32_t idesc = umma_idesc<P>(N);
         const uint32_t a_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
         const uint32_t a_lbo = ((uint32_t)R) << 16, b_lbo = ((uint32_t)N) << 16;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
@@ -169,7 +169,7 @@ tc_up_kernel(const TcUpArgs ua) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * N);
                             const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * a.dil - a.pad - a.min_off);
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<BF16>(acc + (uint32_t)(mt * N), a_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                umma_ksteps<P>(acc + (uint32_t)(mt * N), a_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
                                                   2u * (uint32_t)R, 2u * (uint32_t)N, idesc, ksteps, acc_on | (uint32_t)tt);
                         }
                         tc_commit(W_EMPTY(sw_i));
@@ -224,8 +224,8 @@ tc_up_kernel(const TcUpArgs ua) {
                     uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
                     uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
                     if (valid && a.res) {
-                        load_cells16<BF16>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
-                        if (two) load_cells16<BF16>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
+                        load_cells16<P>(rp + (long long)(ch0 / CW) * a.o_pstride, a.o_pstride, x0);
+                        if (two) load_cells16<P>(rp + (long long)((ch0 + 16) / CW) * a.o_pstride, a.o_pstride, x1);
                     }
                     if (valid && add_prev) {
                         load_f32x16(ap + (long long)(ch0 / 4) * a.acc_pstride, a.acc_pstride, p0);
@@ -260,7 +260,7 @@ tc_up_kernel(const TcUpArgs ua) {
                         if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                            store_cells16<BF16>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
+                            store_cells16<P>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
                         }
                     }
                 }

@@ -84,9 +84,11 @@ class HiFiGANGenerator(nn.Module):
     Shape contract (reference models/hifigan.py:144-147):
         mel [B, n_mels, Tfrm] float32  ->  wav [B, 1, T_wav] float32, T_wav = Tfrm * prod(rates)
 
-    Extra keyword (not in the reference): `mode` in {"fp32", "tf32", "bf16"} --
+    Extra keyword (not in the reference): `mode` in {"fp32", "tf32", "bf16", "fp16"} --
     arithmetic of the CUDA path (include/hfg.h hfg_mode); default from
     $HFG_MODE, else "tf32" (tensor cores, fp32 activations, parity <= 1e-3).
+    "fp16" keeps tf32's 10-bit mantissa (parity <= 1e-3) at bf16's speed; its
+    conversions saturate at +-65504.
     """
 
     def __init__(
