@@ -32,7 +32,7 @@ extern "C" {
 #endif
 
 #define HFG_MAX_STAGES 8
-#define HFG_ABI_VERSION 1
+#define HFG_ABI_VERSION 2
 
 typedef struct hfg_handle hfg_handle;
 
@@ -126,6 +126,23 @@ int hfg_set_mel_layout(hfg_handle* h, int32_t layout);
 int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32_t frames,
                        float* wav_dev, void* workspace_dev, size_t workspace_bytes, int32_t mode,
                        void* stream, float* const* stage_out_dev);
+
+/* Variable-length batch.  The reference has no masks: LengthRegulator pads every
+ * utterance to the batch maximum (reference models/variance_adaptor.py:240-264) and the generator synthesises
+ * the padding.  Here lengths_dev (device, int32 [batch]) gives the valid frame count of each utterance; the
+ * tile schedulers of every kernel skip tiles beyond (length + halo_frames) frames, so padded frames cost
+ * nothing.  Samples [0, T_out(length)) of every utterance are exactly what hfg_forward returns for the same
+ * padded mel (halo_frames must be >= hfg_receptive_radius, else HFG_ERR_INVALID); samples beyond are 0.
+ * Everything, including the per-utterance row counts, is computed on the device: the call stays
+ * asynchronous and graph-capturable. */
+int hfg_forward_lengths(hfg_handle* h, const float* mel_dev, const int32_t* lengths_dev, int32_t halo_frames,
+                        int32_t batch, int32_t frames, float* wav_dev, void* workspace_dev,
+                        size_t workspace_bytes, int32_t mode, void* stream);
+
+/* Receptive radius of one output frame, in mel frames, derived from the configuration (13 for the default
+ * one): time chunking (config 4) and hfg_forward_lengths are exact with a halo of at least this many frames.
+ * Host-only; needs no device. */
+int hfg_receptive_radius(const hfg_config* cfg, int32_t* frames);
 
 /* End-to-end call with HOST buffers: stages mel through pinned memory, copies
  * host->device, runs forward, copies the waveform back and synchronises.

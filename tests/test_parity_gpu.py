@@ -1,11 +1,15 @@
 """Parity tests proper: the CUDA path, called through the C ABI, against the
 committed golden vectors of the live reference and against the oracle.
 
-Tolerances (max-abs on the waveform, whose peak is 0.03-0.07 at random init):
-  fp32  2e-5   fp32 FFMA kernels; only summation order differs from ATen
-  tf32  1e-3   north_star's stated bound for the fp32/TF32 mode
-  bf16  5e-3   bf16 operands + bf16 stored activations (log-mel L1 reported by bench)
+Tolerances (max-abs on the waveform, whose peak is 0.03-0.07 at random init) are about 3x the
+largest value measured on B200 over all cases of this file (profiles/r2_parity.md lists the
+measured numbers, written by the `record` fixture into gpurun_out/parity_r2.jsonl):
+  fp32  5e-7   fp32 FFMA kernels; only summation order differs from ATen           (measured <= 6e-8)
+  tf32  1e-4   tcgen05 kind::tf32; north_star's bound for this mode is 1e-3        (measured <= 3.0e-5)
+  fp16  2e-4   fp16 operands and stored activations, fp32 accumulate; bound 1e-3
+  bf16  1.2e-3 bf16 operands + bf16 stored activations (log-mel L1 reported by bench) (measured <= 4.0e-4)
 """
+import json
 import os
 
 import numpy as np
@@ -19,8 +23,22 @@ from conftest import case_inputs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp32", "tf32", "bf16"]
-TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 5e-3}
+MODES = ["fp32", "tf32", "fp16", "bf16"]
+TC_MODES = ["tf32", "fp16", "bf16"]
+TOL = {"fp32": 5e-7, "tf32": 1e-4, "fp16": 2e-4, "bf16": 1.2e-3}
+NORTH_STAR_BOUND = 1e-3            # fp32 / tf32 / fp16 modes must stay below this whatever TOL says
+
+
+@pytest.fixture
+def record():
+    """Append one measured parity figure to gpurun_out/parity_r2.jsonl (copied into profiles/ by hand)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def _rec(case, mode, err, peak=None, **kw):
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_r2.jsonl"), "a") as f:
+            f.write(json.dumps(dict(case=case, mode=mode, max_abs=err, ref_peak=peak, **kw)) + "\n")
+    return _rec
 CASES = ["default_b2_t24", "default_stages_b1_t9", "default_weightnorm_b1_t16",
          "default_ragged_b3_t7", "odd_upsample_b1_t20", "small_custom_b3_t33",
          "default_config1_b1_t256"]
@@ -41,7 +59,7 @@ def run(gen, mel, stages=None):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", CASES)
-def test_matches_reference_golden(manifest, name, mode):
+def test_matches_reference_golden(manifest, name, mode, record):
     cfg, sd, mel = case_inputs(manifest, name)
     g = load_golden(name)
     gen = make_gen(cfg, sd, mode)
@@ -50,12 +68,13 @@ def test_matches_reference_golden(manifest, name, mode):
     err = float(np.abs(wav - g["wav"]).max())
     rel = err / float(np.abs(g["wav"]).max())
     print(f"{name}[{mode}] max-abs {err:.3e} rel-to-peak {rel:.3e} launches {gen.last_launch_count}")
+    record(name, mode, err, float(np.abs(g["wav"]).max()))
     assert err <= TOL[mode]
     assert gen.last_launch_count > 0
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_saturated_tanh(manifest, mode):
+def test_saturated_tanh(manifest, mode, record):
     """Weights scaled 2.25x drive a quarter of the samples past |0.9|: the pre-tanh
     signal is O(1), so operand rounding shows up un-attenuated."""
     cfg, sd, mel = case_inputs(manifest, "default_saturated_b1_t16")
@@ -63,8 +82,11 @@ def test_saturated_tanh(manifest, mode):
     wav = run(make_gen(cfg, sd, mode), mel)
     err = float(np.abs(wav - g["wav"]).max())
     print(f"saturated[{mode}] max-abs {err:.3e}")
+    record("default_saturated_b1_t16", mode, err, float(np.abs(g["wav"]).max()))
     assert np.abs(wav).max() <= 1.0
-    assert err <= {"fp32": 2e-4, "tf32": 2e-2, "bf16": 1.5e-1}[mode]
+    # signal peak 1.0 here (25x the other cases): bounds are the per-mode TOL scaled by the growth of the
+    # pre-tanh signal, to be tightened to 3x the measured values recorded above
+    assert err <= {"fp32": 2e-5, "tf32": 5e-3, "fp16": 1e-2, "bf16": 6e-2}[mode]
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -78,7 +100,7 @@ def test_stage_boundaries(manifest, mode):
     run(make_gen(cfg, sd, mode), mel, stages=stages)
     stride = manifest["stage_stride"]
     assert len(stages) == 2 * len(cfg["upsample_rates"]) + 1
-    rtol = {"fp32": 1e-5, "tf32": 4e-3, "bf16": 3e-2}[mode]
+    rtol = {"fp32": 1e-5, "tf32": 4e-3, "fp16": 6e-3, "bf16": 3e-2}[mode]
     for i, s in enumerate(stages):
         s = s.cpu().numpy()
         ref = g[f"stage{i}"]
@@ -89,8 +111,8 @@ def test_stage_boundaries(manifest, mode):
         assert err <= rtol * peak, (i, err, peak)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
-def test_config2_against_oracle(mode):
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "fp16"])
+def test_config2_against_oracle(mode, record):
     """BASELINE.json configs[1]: batch 16 x 172 frames, fp32/TF32, <= 1e-3."""
     import oracle
     cfg = synth.DEFAULT_CONFIG
@@ -101,8 +123,9 @@ def test_config2_against_oracle(mode):
     wav = run(make_gen(cfg, sd, mode), mel)
     err = float(np.abs(wav - ref).max())
     print(f"config2[{mode}] max-abs {err:.3e} rel-to-peak {err / np.abs(ref).max():.3e}")
+    record("config2_16x172", mode, err, float(np.abs(ref).max()))
     assert wav.shape == (16, 1, 172 * 256)
-    assert err <= min(1e-3, TOL[mode] * 5)
+    assert err <= TOL[mode] <= NORTH_STAR_BOUND
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -132,7 +155,7 @@ def test_batch_independence_and_determinism(mode):
         assert np.array_equal(one[0], a[i])           # no cross-utterance state
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_concurrent_resblock_streams_equal_serial_run(mode):
     """The tensor-core path runs the resblocks of an MRF on three streams (fork / join with events);
     with per-launch profiling on it serialises them on the caller's stream.  Same bits either way,
@@ -169,7 +192,7 @@ def test_host_buffer_path_equals_device_path(mode):
     assert np.array_equal(host.numpy(), dev)
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_host_path_graph_replay_and_invalidation(mode):
     """hfg_forward_host captures the launch sequence into a CUDA graph on the second call with the same
     geometry and replays it afterwards: replays must equal the device path bit for bit, survive a
@@ -192,20 +215,29 @@ def test_host_path_graph_replay_and_invalidation(mode):
             assert np.array_equal(gen(torch.from_numpy(mel_a)).numpy(), dev_a2)
 
 
-@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("mode", TC_MODES)
 def test_kernel_variants_are_bit_identical(mode):
     """The launch plan picks between kernels that implement the same arithmetic in the same order
-    (persistent vs one-shot conv kernel, polyphase phases stacked along N or one phase per CTA, fused pair
-    vs two convolutions, one stream vs three).  The knobs are read once per process, so each variant runs
-    in its own interpreter; all outputs must hash identically."""
+    (persistent vs one-shot conv kernel, polyphase phases stacked along N or one phase per CTA, one stream
+    vs three, CTA pairs or single CTAs, every tile height -- MT = 1 is the split-column epilogue whose
+    pre2 / epi2 column ownership the round-1 advisor found racy).  The knobs exist only in the tuning build
+    (libhfg_b200_tuning.so, -DHFG_TUNING) and are read once per process, so each variant runs in its own
+    interpreter; the first entry is the PRODUCTION library with the same knobs set, which must ignore them.
+    All outputs must hash identically."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    variants = [{}, {"HFG_TC_UP_PERSIST": "0"}, {"HFG_TC_UP_PERSIST": "0", "HFG_TC_UPS_STACK": "0"},
-                {"HFG_TC_UPS_STACK": "1"}, {"HFG_TC_UP_RESBLOCK": "1", "HFG_TC_UP_WIDE": "1"},
-                {"HFG_TC_STREAMS": "1"}, {"HFG_TC_PAIR_CTAS": "1"}]
+    tuning = os.path.join(root, "tts-sambert_hifigan_b200", "lib", "libhfg_b200_tuning.so")
+    assert os.path.exists(tuning), "build() makes the tuning library next to the production one"
+    T = {"HFG_LIB_PATH": tuning}
+    variants = [{"HFG_TC_UP_PERSIST": "0", "HFG_TC_PAIR_CTAS": "1", "HFG_TC_DBG": "16"},       # production: knobs are dead
+                dict(T), dict(T, HFG_TC_UP_PERSIST="0"), dict(T, HFG_TC_UP_PERSIST="0", HFG_TC_UPS_STACK="0"),
+                dict(T, HFG_TC_UPS_STACK="1"), dict(T, HFG_TC_UP_RESBLOCK="1", HFG_TC_UP_WIDE="1"),
+                dict(T, HFG_TC_STREAMS="1"), dict(T, HFG_TC_PAIR_CTAS="1"),
+                dict(T, HFG_TC_PAIR_MT="1"), dict(T, HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"),
+                dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0")]
     hashes = []
     for v in variants:
-        env = dict(os.environ, **v)
+        env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, **v)
         out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
                              env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, out.stderr[-2000:]
@@ -319,7 +351,7 @@ def test_long_form_against_oracle():
     mel = synth.make_mel(9, 1, 80, 1024)
     ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()},
                                torch.from_numpy(mel)).numpy()
-    for mode in ("tf32", "bf16"):
+    for mode in TC_MODES:
         wav = run(make_gen(cfg, sd, mode), mel)
         err = float(np.abs(wav - ref).max())
         print(f"long-form[{mode}] max-abs {err:.3e}")
@@ -344,7 +376,7 @@ def test_geometry_outside_umma_shapes_falls_back_to_fp32_kernels():
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_config5_acoustic_model_output_feeds_generator(mode):
+def test_config5_acoustic_model_output_feeds_generator(mode, record):
     """BASELINE.json configs[4]: mel_pred [B, Tfrm, 80] produced by the UNMODIFIED reference SAM-BERT
     acoustic model (tests/golden/make_config5.py) -> new generator.  The integer frame indexing
     (duration rounding + repeat_interleave, reference models/variance_adaptor.py:232,746-748) is the
@@ -369,23 +401,93 @@ def test_config5_acoustic_model_output_feeds_generator(mode):
                                torch.from_numpy(mel_pred).transpose(1, 2).contiguous()).numpy()
     err = float(np.abs(a.cpu().numpy() - ref).max())
     print(f"config5[{mode}] Tfrm {mel_pred.shape[1]} max-abs {err:.3e} peak {np.abs(ref).max():.3e}")
-    assert err <= TOL[mode] * (4 if mode == "bf16" else 1)
+    record("config5_acoustic_b8", mode, err, float(np.abs(ref).max()))
+    assert err <= TOL[mode]
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_ragged_batch_valid_region_is_identical(mode):
-    """a per-utterance length vector lets the path skip padded frames; the
-    valid region of every utterance must equal the reference-style full-length run bit for bit."""
+def test_ragged_batch_against_oracle(mode, record):
+    """the per-utterance length vector goes through the C ABI (hfg_forward_lengths)
+    and the kernels' tile schedulers skip everything beyond length + halo.  Checked against the ORACLE run on
+    the padded batch the way the reference would run it (no masks): the valid region of every utterance is
+    within the mode's tolerance of the oracle, bit-identical to this library's own full-length run, and the
+    rest of the row is zeros.  The workspace is pre-filled with NaN patterns: skipped tiles must not leak."""
+    import oracle
     cfg = synth.DEFAULT_CONFIG
-    gen = make_gen(cfg, synth.make_weights(cfg, 6), mode)
+    sd = synth.make_weights(cfg, 6)
+    gen = make_gen(cfg, sd, mode)
     lens = [169, 297, 393, 214, 40, 185, 323, 1]                      # config-5-like raggedness
-    mel = torch.from_numpy(synth.make_mel(13, len(lens), 80, max(lens))).to("cuda:0")
+    mel_np = synth.make_mel(13, len(lens), 80, max(lens))
+    mel = torch.from_numpy(mel_np).to("cuda:0")
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel_np)).numpy()
     with torch.no_grad():
         full = gen(mel)                                               # what the reference does: no masks
+        for ws in gen._workspaces.values():
+            ws.fill_(0xFF)
         rag = gen.forward_ragged(mel, lens)
+        n_rag = gen.last_launch_count
     torch.cuda.synchronize()
     assert rag.shape == full.shape
+    rag_np = rag.cpu().numpy()
+    worst = 0.0
     for i, n in enumerate(lens):
         assert torch.equal(rag[i, :, : n * 256], full[i, :, : n * 256]), i
+        assert float(rag[i, :, n * 256:].abs().max()) == 0.0 if n < max(lens) else True
+        worst = max(worst, float(np.abs(rag_np[i, :, : n * 256] - ref[i, :, : n * 256]).max()))
+    print(f"ragged[{mode}] valid-region max-abs vs oracle {worst:.3e}, launches {n_rag}")
+    record("ragged_b8_vs_oracle", mode, worst, float(np.abs(ref).max()))
+    assert np.isfinite(rag_np).all()
+    assert worst <= TOL[mode]
     with pytest.raises(RuntimeError):
         gen.forward_ragged(mel, lens[:-1])
+    with pytest.raises(ValueError, match="receptive radius"):
+        gen.forward_ragged(mel, lens, halo=5)
+    assert gen.receptive_radius == 13
+
+
+def test_ragged_batch_throughput_win():
+    """The point of the length vector: a config-5-like batch (8 utterances, 1 .. 393 frames, mean 208)
+    costs about the work of its valid frames, not of 8 x 393 padded ones."""
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 6), "bf16")
+    lens = [169, 297, 393, 214, 40, 185, 323, 1]
+    mel = torch.from_numpy(synth.make_mel(13, len(lens), 80, max(lens))).to("cuda:0")
+
+    def timed(fn, n=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    with torch.no_grad():
+        t_full = timed(lambda: gen(mel))
+        t_rag = timed(lambda: gen.forward_ragged(mel, lens))
+    frac = (sum(lens) + 14 * len(lens)) / (max(lens) * len(lens))
+    print(f"ragged throughput: padded {t_full:.3f} ms, length-aware {t_rag:.3f} ms "
+          f"({t_full / t_rag:.2f}x; valid+halo frames are {frac:.2f} of the padded ones)")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/ragged_r2.json", "w") as f:
+        json.dump({"lens": lens, "padded_ms": t_full, "length_aware_ms": t_rag, "valid_plus_halo_frac": frac}, f)
+    assert t_rag < t_full
+
+
+def test_fp32_frames_last_with_more_mels_than_channels():
+    """Round-1 advisor: with n_mels > every stage's channels x time per frame, the transposed mel of the fp32
+    frames-last path used to overrun its scratch buffer.  n_mels = 80 into 16 channels."""
+    import oracle
+    cfg = dict(n_mels=80, upsample_rates=[2, 2], upsample_kernel_sizes=[4, 4], upsample_initial_channel=16,
+               resblock_kernel_sizes=[3], resblock_dilation_sizes=[[1, 3]])
+    sd = synth.make_weights(cfg, 31)
+    mel = synth.make_mel(32, 2, 80, 50)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    gen = make_gen(cfg, sd, "fp32")
+    x = torch.from_numpy(mel).to("cuda:0").transpose(1, 2).contiguous()          # [B, T, 80]
+    with torch.no_grad():
+        wav = gen.forward_frames_last(x)
+    torch.cuda.synchronize()
+    assert float(np.abs(wav.cpu().numpy() - ref).max()) <= 2e-6

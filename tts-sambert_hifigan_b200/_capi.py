@@ -19,6 +19,7 @@ SYMBOLS = [
     "hfg_forward_stages", "hfg_forward_host", "hfg_forward_host_ex", "hfg_last_launch_count",
     "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer", "hfg_set_mel_layout",
     "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
+    "hfg_forward_lengths", "hfg_receptive_radius",
 ]
 
 
@@ -103,6 +104,10 @@ def load():
     lib.hfg_length_regulate_frames.argtypes = [vp, i32, i32, i64p, vp]
     lib.hfg_length_regulate.restype = ctypes.c_int
     lib.hfg_length_regulate.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.hfg_forward_lengths.restype = ctypes.c_int
+    lib.hfg_forward_lengths.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, ctypes.c_size_t, i32, vp]
+    lib.hfg_receptive_radius.restype = ctypes.c_int
+    lib.hfg_receptive_radius.argtypes = [ctypes.POINTER(HfgConfig), ctypes.POINTER(ctypes.c_int32)]
     lib.hfg_bench_layer.restype = ctypes.c_int
     lib.hfg_bench_layer.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, fp]
     del fp
@@ -134,6 +139,15 @@ def make_config(n_mels: int, upsample_rates: Sequence[int], upsample_kernel_size
         for l, d in enumerate(dils):
             c.resblock_dilations[j][l] = int(d)
     return c
+
+
+def receptive_radius(cfg: HfgConfig) -> int:
+    """Receptive radius of one output frame in mel frames (host-only, no device needed)."""
+    out = ctypes.c_int32()
+    rc = load().hfg_receptive_radius(ctypes.byref(cfg), ctypes.byref(out))
+    if rc != OK:
+        raise HfgError(rc, "invalid generator configuration")
+    return out.value
 
 
 class Handle:
@@ -190,6 +204,11 @@ class Handle:
             rc = self._lib.hfg_forward_stages(self._h, mel_ptr, batch, frames, wav_ptr, ws_ptr, ws_bytes,
                                               mode, ctypes.c_void_p(stream), arr)
         self._check(rc)
+
+    def forward_lengths(self, mel_ptr: int, lengths_ptr: int, halo: int, batch: int, frames: int, wav_ptr: int,
+                        ws_ptr: int, ws_bytes: int, mode: int, stream: int):
+        self._check(self._lib.hfg_forward_lengths(self._h, mel_ptr, lengths_ptr, halo, batch, frames, wav_ptr,
+                                                  ws_ptr, ws_bytes, mode, ctypes.c_void_p(stream)))
 
     def forward_host(self, mel_ptr: int, batch: int, frames: int, wav_ptr: int, mode: int,
                      mel_pinned: bool = False, wav_pinned: bool = False):

@@ -229,14 +229,15 @@ static ConvArgs conv_args(const ConvLayer& L, const float* x, float* y, int T, f
     return a;
 }
 
+static size_t workspace_fp32(const hfg_handle* h, int B, int T);
+static size_t fp32_buffer_stride(const hfg_handle* h, int B, int T);
+
 static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws,
-                         cudaStream_t st, float* const* stage_out) {
+                         cudaStream_t st, float* const* stage_out, const int* lengths, int halo) {
     std::vector<int> C;
     std::vector<int64_t> L;
     stage_geometry(h, T, C, L);
-    size_t emax = 0;
-    for (size_t i = 0; i < C.size(); ++i) emax = std::max(emax, (size_t)B * C[i] * L[i]);
-    const size_t stride = (emax * sizeof(float) + 255) / 256 * 256;
+    const size_t stride = fp32_buffer_stride(h, B, T);
     float* bufX = (float*)(ws);
     float* bufR = (float*)(ws + stride);
     float* bufH = (float*)(ws + 2 * stride);
@@ -312,16 +313,37 @@ static void forward_fp32(hfg_handle* h, const float* mel, int B, int T, float* w
     conv_post_tanh_fp32<<<grid, 256, sizeof(float) * p.Cin * p.k, st>>>(p);
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "conv_post launch");
+    if (lengths) {
+        // variable-length batch in the strict mode: everything is generated, samples beyond each utterance's
+        // valid length are zeroed (the tensor-core modes skip those tiles instead)
+        int* tab = reinterpret_cast<int*>(ws + 5 * stride);
+        LenGeom g{};
+        g.n_stages = (int)h->ups.size();
+        for (int i = 0; i < g.n_stages; ++i) { g.u[i] = h->ups[i].u; g.k[i] = h->ups[i].k; g.p[i] = h->ups[i].p; }
+        h->prof_begin(st, "len_table", 0, 0);
+        tc_len_table<<<(B + 127) / 128, 128, 0, st>>>(lengths, B, T, halo, g, tab);
+        h->prof_end(st);
+        h->prof_begin(st, "mask_tail", 0, 0);
+        tc_mask_tail<<<dim3((p.T + 255) / 256, B), 256, 0, st>>>(wav, tab + (size_t)(1 + g.n_stages) * B, p.T);
+        h->prof_end(st);
+        check_cuda(cudaGetLastError(), "mask_tail launch");
+    }
 }
 
-static size_t workspace_fp32(const hfg_handle* h, int B, int T) {
+// elements of the largest activation; the frames-last path also stages the transposed mel in a buffer
+static size_t fp32_buffer_stride(const hfg_handle* h, int B, int T) {
     std::vector<int> C;
     std::vector<int64_t> L;
     stage_geometry(h, T, C, L);
-    size_t emax = 0;
+    size_t emax = (size_t)B * h->cfg.n_mels * T;
     for (size_t i = 0; i < C.size(); ++i) emax = std::max(emax, (size_t)B * C[i] * L[i]);
-    const size_t stride = (emax * sizeof(float) + 255) / 256 * 256;
-    return 5 * stride;
+    return (emax * sizeof(float) + 255) / 256 * 256;
+}
+static size_t fp32_lens_bytes(const hfg_handle* h, int B) {
+    return ((size_t)(h->ups.size() + 2) * B * sizeof(int) + 255) / 256 * 256;
+}
+static size_t workspace_fp32(const hfg_handle* h, int B, int T) {
+    return 5 * fp32_buffer_stride(h, B, T) + fp32_lens_bytes(h, B);
 }
 
 static void validate_config(const hfg_config& c) {
@@ -346,8 +368,37 @@ static void validate_config(const hfg_config& c) {
     }
 }
 
+// Receptive radius of one output frame in mel frames: the interval of wav samples [f*hop, (f+1)*hop) is
+// propagated backwards through conv_post, every MRF (widest resblock), every ConvTranspose1d and conv_pre
+// (reference models/hifigan.py:224-261).  13 for the default configuration.
+static int receptive_radius(const hfg_config& c) {
+    long long hop = 1;
+    for (int i = 0; i < c.num_upsamples; ++i) hop *= c.upsample_rates[i];
+    const long long f = 1 << 20;                            // far from both edges
+    long long lo = f * hop, hi = (f + 1) * hop - 1;
+    lo -= 3; hi += 3;                                       // conv_post, k = 7
+    auto floor_div = [](long long a, long long b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+    for (int i = c.num_upsamples - 1; i >= 0; --i) {
+        long long r = 0;
+        for (int j = 0; j < c.num_resblocks; ++j) {
+            long long rj = 0;
+            const int k = c.resblock_kernel_sizes[j];
+            for (int l = 0; l < c.num_dilations[j]; ++l) rj += (long long)c.resblock_dilations[j][l] * (k - 1) / 2 + (k - 1) / 2;
+            r = std::max(r, rj);
+        }
+        lo -= r; hi += r;
+        const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i], p = (k - u) / 2;
+        // output t reads input q iff 0 <= t + p - q*u < k
+        lo = -floor_div(-(lo + p - (k - 1)), u);            // ceil((lo + p - k + 1) / u)
+        hi = floor_div(hi + p, u);
+    }
+    lo -= 3; hi += 3;                                       // conv_pre, k = 7
+    return (int)std::max(f - lo, hi - f);
+}
+
 static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav, void* ws,
-                       size_t ws_bytes, int mode, cudaStream_t st, float* const* stage_out) {
+                       size_t ws_bytes, int mode, cudaStream_t st, float* const* stage_out,
+                       const int* lengths = nullptr, int halo = 0) {
     if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed (call hfg_commit_weights)");
     if (!mel || !wav) throw StatusError(HFG_ERR_INVALID, "null mel/wav pointer");
     if (B <= 0 || T <= 0) throw StatusError(HFG_ERR_INVALID, "batch and frames must be positive");
@@ -361,8 +412,11 @@ static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
     h->launches = 0;
     h->prof.clear();
     h->events_used = 0;
-    if (mode == HFG_MODE_FP32) forward_fp32(h, mel, B, T, wav, (char*)ws, st, stage_out);
-    else tc_forward(h, mel, B, T, wav, (char*)ws, mode, st, stage_out);
+    if (lengths && halo < receptive_radius(h->cfg))
+        throw StatusError(HFG_ERR_INVALID, "halo_frames is smaller than the receptive radius of this configuration (" +
+                                               std::to_string(receptive_radius(h->cfg)) + " frames): the valid region would change");
+    if (mode == HFG_MODE_FP32) forward_fp32(h, mel, B, T, wav, (char*)ws, st, stage_out, lengths, halo);
+    else tc_forward(h, mel, B, T, wav, (char*)ws, mode, st, stage_out, lengths, halo);
 }
 
 }  // namespace hfg
@@ -501,6 +555,28 @@ int hfg_forward_stages(hfg_handle* h, const float* mel_dev, int32_t batch, int32
     do_forward(h, mel_dev, batch, frames, wav_dev, workspace_dev, workspace_bytes, mode,
                (cudaStream_t)stream, stage_out_dev);
     HFG_CATCH(h)
+}
+
+int hfg_forward_lengths(hfg_handle* h, const float* mel_dev, const int32_t* lengths_dev, int32_t halo_frames,
+                        int32_t batch, int32_t frames, float* wav_dev, void* workspace_dev, size_t workspace_bytes,
+                        int32_t mode, void* stream) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!lengths_dev) throw StatusError(HFG_ERR_INVALID, "hfg_forward_lengths: null lengths pointer");
+    do_forward(h, mel_dev, batch, frames, wav_dev, workspace_dev, workspace_bytes, mode, (cudaStream_t)stream,
+               nullptr, lengths_dev, halo_frames);
+    HFG_CATCH(h)
+}
+
+int hfg_receptive_radius(const hfg_config* cfg, int32_t* frames) {
+    if (!cfg || !frames) return HFG_ERR_INVALID;
+    try {
+        validate_config(*cfg);
+    } catch (...) {
+        return HFG_ERR_INVALID;
+    }
+    *frames = receptive_radius(*cfg);
+    return HFG_OK;
 }
 
 int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,

@@ -144,8 +144,10 @@ struct hfg_handle {
         check_cuda(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest), "cudaDeviceGetStreamPriorityRange");
         for (int i = 0; i < kStreams - 1; ++i)
             check_cuda(cudaStreamCreateWithPriority(&side[i], cudaStreamNonBlocking,
-                                                    getenv("HFG_TC_STREAM_NOPRIO") ? prio_least
-                                                        : std::max(prio_greatest, prio_least - 1 - i)),
+#ifdef HFG_TUNING
+                                                    getenv("HFG_TC_STREAM_NOPRIO") ? prio_least :
+#endif
+                                                    std::max(prio_greatest, prio_least - 1 - i)),
                        "cudaStreamCreateWithPriority");
         check_cuda(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "cudaEventCreate");
         for (auto& e : ev_join) check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");

@@ -36,6 +36,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/hfg.h"
+
 namespace hfg {
 
 constexpr int kTcEpiWarps = 8;                       // two warps per TMEM lane quarter, splitting the column steps
@@ -92,6 +94,7 @@ struct TcConvArgs {
     int tap_group;      // taps per W stage (small layers: fewer, fatter stages)
     int tiles_per_batch;
     float slope;        // leaky_relu slope fused on the OUTPUT (and inverted on the residual)
+    const int* len_rows;            // variable-length batches: output rows utterance b needs, or null (see tc_len_nq)
     unsigned long long* timeline;   // tuning only: clock64 stamps of the first 64 CTAs along grid.y, [cta][8 events]
 };
 #ifndef HFG_TUNING
@@ -103,6 +106,12 @@ struct TcConvArgs {
             a.timeline[(size_t)blockIdx.y * 8 + (ev)] = (unsigned long long)clock64();                \
     } while (0)
 #endif
+
+// q positions (input rows / GEMM rows) needed for `len_out` output rows: t = q * out_stride + phase + out_off
+__device__ __forceinline__ int tc_len_nq(const TcConvArgs& a, int len_out) {
+    const int nq = (len_out - 1 - a.out_off) / a.out_stride + 1;
+    return nq < a.n_q ? nq : a.n_q;
+}
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -402,6 +411,10 @@ tc_conv_kernel(const TcConvArgs a) {
     constexpr int CW = Prec<P>::CW;       // channels per 16-byte cell
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a.len_rows) {                                      // tile beyond its utterance's length: nothing to do
+        const int tb = blockIdx.y / a.tiles_per_batch;
+        if ((int)(blockIdx.y % a.tiles_per_batch) * a.MT * 128 >= tc_len_nq(a, a.len_rows[tb])) return;
+    }
     if (warp == 0) HFG_CONV_TL(0);
     const int N = a.N, MT = a.MT, R = a.R;
     const int nck_max = a.a_nchunks < 8 ? a.a_nchunks : 8;
@@ -685,6 +698,32 @@ __global__ void tc_zero_pads(const PadJobs jobs) {
     }
 }
 
+// Variable-length batches: per-utterance row counts of every stage, from the valid frame counts.
+//   tab[0][b]      = min(T, len_b + halo)                    frames read by conv_pre
+//   tab[1+i][b]    = rows of stage i (after ups[i]) for those frames
+//   tab[1+n][b]    = waveform samples of the len_b valid frames (no halo): everything beyond is returned as 0
+struct LenGeom { int n_stages; int u[HFG_MAX_STAGES], k[HFG_MAX_STAGES], p[HFG_MAX_STAGES]; };
+__global__ void tc_len_table(const int* __restrict__ lengths, int B, int T, int halo, const LenGeom g, int* __restrict__ tab) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int len = lengths[b];
+    len = len < 0 ? 0 : (len > T ? T : len);
+    long long eff = len + halo < T ? len + halo : T, val = len;
+    tab[b] = (int)eff;
+    for (int i = 0; i < g.n_stages; ++i) {
+        eff = eff > 0 ? (eff - 1) * g.u[i] - 2 * g.p[i] + g.k[i] : 0;
+        val = val > 0 ? (val - 1) * g.u[i] - 2 * g.p[i] + g.k[i] : 0;
+        tab[(size_t)(1 + i) * B + b] = (int)eff;
+    }
+    tab[(size_t)(1 + g.n_stages) * B + b] = (int)val;
+}
+// fp32 mode: the full batch is generated; samples beyond the valid length are zeroed afterwards
+__global__ void tc_mask_tail(float* __restrict__ y, const int* __restrict__ valid_len, int T) {
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T && t >= valid_len[b]) y[(size_t)b * T + t] = 0.f;
+}
+
 // conv_post (C_out = 1, K taps) + tanh from chunk planes that already hold leaky_relu(x)
 // (reference models/hifigan.py:254-256).  HBM-bound: reads C channels per step, writes one sample.
 // A block stages (kPostTile + K - 1) rows x C/CW cells in shared memory with coalesced 16-byte loads (each
@@ -696,7 +735,8 @@ constexpr int kPostThreads = 128, kPostR = 4, kPostTile = kPostThreads * kPostR,
 template <int P, int K>
 __global__ void __launch_bounds__(kPostThreads)
 tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                  float* __restrict__ y, int C, int T, int pad, long long bstride, long long pstride) {
+                  float* __restrict__ y, int C, int T, int pad, long long bstride, long long pstride,
+                  const int* __restrict__ len_rows, const int* __restrict__ valid_len) {
     constexpr int CW = Prec<P>::CW;
     constexpr int ROWS = kPostTile + K - 1;
     extern __shared__ __align__(16) uint8_t post_smem[];
@@ -709,6 +749,13 @@ tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, c
     }
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kPostTile;
+    // variable-length batches: samples at or beyond valid_len[b] are zeros; tiles beyond the rows that were
+    // generated for utterance b (len_rows[b] = valid + halo) are not even read
+    const int Tv = valid_len ? (valid_len[b] < T ? valid_len[b] : T) : T;
+    if (len_rows && t0 >= len_rows[b]) {
+        for (int e = threadIdx.x; e < kPostTile && t0 + e < T; e += blockDim.x) y[(size_t)b * T + t0 + e] = 0.f;
+        return;
+    }
     // rows t0 - pad .. t0 - pad + ROWS: the planes carry kPadL zero rows in front of the data and the tile
     // overhang behind it (tc_tp); rows past T + kZeroTail may hold anything but only feed samples >= T
     const uint8_t* base = in + (long long)b * bstride + (long long)(kPadL + t0 - pad) * 16;
@@ -750,13 +797,15 @@ tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, c
     }
     const float bv = bias[0];
     const size_t o = (size_t)b * T + t0 + tl;
+    float out[kPostR];
+#pragma unroll
+    for (int r = 0; r < kPostR; ++r) out[r] = (t0 + tl + r < Tv) ? tanhf(acc[r] + bv) : 0.f;
     if (t0 + tl + kPostR <= T && (o & 3) == 0) {
-        *reinterpret_cast<float4*>(y + o) =
-            make_float4(tanhf(acc[0] + bv), tanhf(acc[1] + bv), tanhf(acc[2] + bv), tanhf(acc[3] + bv));
+        *reinterpret_cast<float4*>(y + o) = make_float4(out[0], out[1], out[2], out[3]);
     } else {
 #pragma unroll
         for (int r = 0; r < kPostR; ++r)
-            if (t0 + tl + r < T) y[o + r] = tanhf(acc[r] + bv);
+            if (t0 + tl + r < T) y[o + r] = out[r];
     }
 }
 

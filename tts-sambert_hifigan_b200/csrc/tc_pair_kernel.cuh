@@ -60,6 +60,9 @@ struct TcPairArgs {
     int poll_ns;      // producer back-off when both rings are full
     int dbg;          // HFG_TUNING builds only -- timing experiments (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
     int tiles_per_batch, n_tiles;
+    // variable-length batches: rows of this stage that utterance b needs (valid frames + receptive halo, scaled to
+    // this stage), or null.  Tiles that start at or beyond len_rows[b] are never loaded, multiplied or stored.
+    const int* len_rows;
     float slope;
     unsigned long long* timeline;   // tuning only (tools/pair_timeline.py): clock64 stamps, [cta < 4][tile < 16][event < 16]
 };
@@ -165,7 +168,22 @@ tc_pair_kernel(const TcPairArgs a) {
     const int n_sched = (a.n_tiles + CTAS - 1) / CTAS;
     const int sched0 = (int)blockIdx.x / CTAS, sched_step = (int)gridDim.x / CTAS;
     auto tile_of = [&](int sc) { const int t = sc * CTAS + (int)rank; return t < a.n_tiles ? t : a.n_tiles - 1; };
-    auto tile_real = [&](int sc) { return sc * CTAS + (int)rank < a.n_tiles; };
+    auto tile_live = [&](int t) {                      // inside the batch and not beyond its utterance's length
+        if (t >= a.n_tiles) return false;
+        if (!a.len_rows) return true;
+        return (t % a.tiles_per_batch) * a.TO < a.len_rows[t / a.tiles_per_batch];
+    };
+    auto tile_real = [&](int sc) { return tile_live(sc * CTAS + (int)rank); };
+    // a schedule slot runs when any of its CTAS tiles is live; the other CTA of a pair then runs its (dead)
+    // tile with stores suppressed, exactly like the duplicated odd tail tile.  Every role of both CTAs
+    // evaluates this predicate on the same data, so they skip the same slots.
+    auto sched_live = [&](int sc) {
+        if (!a.len_rows) return true;
+        for (int r = 0; r < CTAS; ++r)
+            if (tile_live(sc * CTAS + r)) return true;
+        return false;
+    };
+    auto next_live = [&](int sc) { while (sc < n_sched && !sched_live(sc)) sc += sched_step; return sc; };
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -180,20 +198,20 @@ tc_pair_kernel(const TcPairArgs a) {
         // one polling thread: whichever ring has a free slot gets its next copy.  (Issuing them in one
         // blocking program order let a full A ring stall the weight stream and starve the MMAs:
         // profiles/r1_tuning.md section 6.)
-        const int n_my = sched0 < n_sched ? (n_sched - sched0 + sched_step - 1) / sched_step : 0;
         const int groups = (k + G - 1) / G;
-        int a_t = 0, a_kb = 0;                                   // next A block: tile ordinal, K block
-        int w_t = 0, w_conv = 0, w_kb = 0, w_g = 0;              // next W stage
+        int a_sc = next_live(sched0), a_kb = 0;                  // next A block: schedule slot, K block
+        int w_sc = a_sc, w_conv = 0, w_kb = 0, w_g = 0;          // next W stage
+        int a_t = 0, w_t = 0;                                    // ordinals of those slots among this CTA's live ones
         uint32_t idle = 0;
         long long t_idle0 = 0;
-        while (a_t < n_my || w_t < n_my) {
+        while (a_sc < n_sched || w_sc < n_sched) {
             bool did = false;
-            if (a_t < n_my && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
+            if (a_sc < n_sched && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
                 if (a_kb == 0) HFG_TL(0, a_t);
                 if (leader && HFG_DBG(a, 2)) mbar_arrive(A_FULL(sa_i));
                 if (leader && !HFG_DBG(a, 2)) {
-                    const uint8_t* ab = tile_src(tile_of(sched0 + a_t * sched_step));
+                    const uint8_t* ab = tile_src(tile_of(a_sc));
                     mbar_expect_tx(A_FULL(sa_i), (uint32_t)nck * R1 * 16);
                     const uint32_t dst = smem_u32(sA + (size_t)sa_i * a_stage_bytes);
                     for (int c = 0; c < nck; ++c)
@@ -202,10 +220,10 @@ tc_pair_kernel(const TcPairArgs a) {
                 }
                 __syncwarp();
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
-                if (++a_kb == n_kb) { a_kb = 0; ++a_t; }
+                if (++a_kb == n_kb) { a_kb = 0; ++a_t; a_sc = next_live(a_sc + sched_step); }
                 did = true;
             }
-            if (w_t < n_my && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
+            if (w_sc < n_sched && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * w_kb) < KBC ? (n_chunks - KBC * w_kb) : KBC;
                 const int tap0 = w_g * G;
                 const int g = (k - tap0) < G ? (k - tap0) : G;
@@ -221,7 +239,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 }
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                if (++w_g == groups) { w_g = 0; if (++w_kb == n_kb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; } } }
+                if (++w_g == groups) { w_g = 0; if (++w_kb == n_kb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
                 did = true;
             }
             if (did) { idle = 0; t_idle0 = 0; continue; }
@@ -242,7 +260,8 @@ tc_pair_kernel(const TcPairArgs a) {
         if (CTAS == 2 && rank == 1) {
             // ---- peer CTA: no MMA issue.  Forward "my stage has landed" to the leader: one lane per ring
             // slot, so slots are forwarded independently instead of through one serial wait chain ----
-            const int n_my = sched0 < n_sched ? (n_sched - sched0 + sched_step - 1) / sched_step : 0;
+            int n_my = 0;
+            for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step)) ++n_my;
             const int stages_per_tile = 2 * n_kb * ((k + G - 1) / G);
             const int total_w = n_my * stages_per_tile, total_a = n_my * n_kb;
             if (lane < a.sw) {
@@ -264,7 +283,7 @@ tc_pair_kernel(const TcPairArgs a) {
         const uint32_t h_lo_base = ((smem_u32(sH) & 0x3FFFFu) >> 4) | h_lbo;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t it = 0;
-        for (int sc = sched0; sc < n_sched; sc += sched_step, ++it) {
+        for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step), ++it) {
             // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1 ----
             uint32_t acc_on = 0;
             for (int kb = 0; kb < n_kb; ++kb) {
@@ -350,7 +369,7 @@ tc_pair_kernel(const TcPairArgs a) {
         const bool acc_store_mode = (a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD);
         int sa_i = 0, sa_ph = 0;
         uint32_t it = 0;
-        for (int sc = sched0; sc < n_sched; sc += sched_step, ++it) {
+        for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step), ++it) {
             const int tile = tile_of(sc);
             const bool real = tile_real(sc);          // false: duplicated tail tile, no global side effects
             const int b = tile / a.tiles_per_batch;

@@ -236,6 +236,7 @@ struct TcPlan {
     // planes R, H.  Only where a pair does not fit the fused kernel: a scratch S for its intermediate, and an
     // fp32 running-sum plane ACC if that pair is the one that forms the MRF sum.
     struct Stage { TcPlane X, Y, ACC; bool sum_planes = false; struct { TcPlane R, H, S; bool fused = true; } rb[HFG_MAX_STAGES]; } st[HFG_MAX_STAGES];
+    size_t lens_off = 0;                    // int32 [(num_upsamples + 2)][B]: per-utterance row counts (tc_len_table)
     size_t total = 0;
 };
 
@@ -269,6 +270,8 @@ static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
         }
         if (!S.sum_planes && n_rb > 1) S.ACC = tc_plane(B, U.cout, t, 4, cur);          // fp32 accumulator cells
     }
+    p.lens_off = cur;
+    cur += ((size_t)(h->ups.size() + 2) * B * sizeof(int) + 255) / 256 * 256;
     p.total = cur;
     return p;
 }
@@ -324,7 +327,11 @@ static void tc_launch_conv(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, 
     dim3 grid(a.phases * (cout / a.N), B * a.tiles_per_batch, 1);
     // tuning only: HFG_TC_CONV_TIMELINE="<label>:<file>" stamps the phases of the first 64 CTAs of that launch
     unsigned long long* tl_dev = nullptr;
+#ifdef HFG_TUNING
     const char* tl_env = getenv("HFG_TC_CONV_TIMELINE");
+#else
+    const char* tl_env = nullptr;
+#endif
     const char* tl_path = nullptr;
     if (tl_env) {
         const char* colon = strchr(tl_env, ':');
@@ -530,7 +537,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
                            const uint8_t* in, long long in_b, long long in_p, int n_chunks,
                            uint8_t* out, long long out_b, long long out_p,
                            float* acc, long long acc_b, long long acc_p, int acc_mode, float div,
-                           const uint8_t* const* sum_in, int n_sum,
+                           const uint8_t* const* sum_in, int n_sum, const int* len_rows,
                            int B, int T, const char* label) {
     constexpr int ESZ = Prec<P>::ESZ;
     TcPairArgs a{};
@@ -552,6 +559,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.R1 = g.R1; a.RH = g.RH; a.TO = g.TO; a.sa = g.sa; a.sw = g.sw; a.tap_group = g.G;
     a.tiles_per_batch = (T + g.TO - 1) / g.TO;
     a.n_tiles = a.tiles_per_batch * B;
+    a.len_rows = len_rows;
     a.slope = 0.1f;
     a.timeline = h->pair_timeline;
     // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
@@ -598,14 +606,26 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
 
 template <int P>
 static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws,
-                            cudaStream_t st, float* const* stage_out) {
+                            cudaStream_t st, float* const* stage_out, const int* lengths, int halo) {
     constexpr int ESZ = Prec<P>::ESZ;
     const TcPlan plan = tc_plan(h, B, T, P == PREC_BF16 ? HFG_MODE_BF16 : (P == PREC_FP16 ? HFG_MODE_FP16 : HFG_MODE_TF32));
     const float slope = 0.1f;
     const int n_rb = h->cfg.num_resblocks;
     auto ptr = [&](const TcPlane& p) { return reinterpret_cast<uint8_t*>(ws + p.off); };
+    // variable-length batch: row counts per utterance and stage, computed on the device from `lengths`
+    int* len_tab = lengths ? reinterpret_cast<int*>(ws + plan.lens_off) : nullptr;
+    auto lens_of = [&](int row) -> const int* { return len_tab ? len_tab + (size_t)row * B : nullptr; };
 
     h->stage_begin(st, "head");
+    if (lengths) {
+        LenGeom g{};
+        g.n_stages = (int)h->ups.size();
+        for (int i = 0; i < g.n_stages; ++i) { g.u[i] = h->ups[i].u; g.k[i] = h->ups[i].k; g.p[i] = h->ups[i].p; }
+        h->prof_begin(st, "len_table", 0, 0);
+        tc_len_table<<<(B + 127) / 128, 128, 0, st>>>(lengths, B, T, halo, g, len_tab);
+        h->prof_end(st);
+        check_cuda(cudaGetLastError(), "tc_len_table launch");
+    }
     // ---- zero the padding rows of every plane (one launch) ----
     {
         PadJobs jobs{};
@@ -651,8 +671,9 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         check_cuda(cudaGetLastError(), "tc_unpack_stage launch");
     };
     auto conv = [&](cudaStream_t st, const ConvLayer& L, const TcPlane& in, const TcPlane* out, const TcPlane* res,
-                    const TcPlane* acc, int acc_mode, const char* label) {
+                    const TcPlane* acc, int acc_mode, const char* label, const int* len_rows) {
         TcConvArgs a{};
+        a.len_rows = len_rows;
         a.a = ptr(in); a.a_bstride = in.bstride; a.a_pstride = in.pstride; a.a_nchunks = in.nchunks;
         a.N = tc_pick_n(L.cout);
         a.w = reinterpret_cast<const uint8_t*>(L.tc.w[P]);
@@ -678,7 +699,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     };
 
     // conv_pre (reference :238); its output is stored as leaky_relu(x) for ups[0] (:244)
-    conv(st, h->pre, plan.mel, &plan.pre, nullptr, nullptr, TC_ACC_NONE, "conv_pre");
+    conv(st, h->pre, plan.mel, &plan.pre, nullptr, nullptr, TC_ACC_NONE, "conv_pre", lens_of(0));
     h->stage_end(st);
     dump(0, plan.pre);
 
@@ -708,6 +729,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             a.taps_max = U.taps_max; a.k = U.k; a.u = U.u; a.dil = -1; a.pad = 0; a.phases = stack ? 1 : U.u;
             a.out_stride = U.u; a.out_off = -U.p; a.min_off = -(U.taps_max - 1);
             a.slope = slope;
+            a.len_rows = lens_of(1 + (int)i);
             const double flops = 2.0 * U.cin * U.cout * U.k * (double)B * cur->T;
             const double bytes = (double)B * ESZ * ((double)U.cin * cur->T + (double)U.cout * S.X.T) +
                                  (double)ESZ * U.cin * U.cout * U.k;
@@ -791,11 +813,12 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                                           use_acc ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
                                           S.ACC.bstride, S.ACC.pstride, mode, (float)n_rb,
                                           (sum_planes && closes) ? fin.data() : nullptr, (sum_planes && closes) ? (int)fin.size() : 0,
-                                          B, S.X.T, lab.c_str());
+                                          lens_of(1 + (int)i), B, S.X.T, lab.c_str());
                     } else {
                         // unfused fallback: conv1 -> scratch, conv2 (+ residual) -> dst
-                        conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, lab.c_str());
-                        conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, lab.c_str());
+                        conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, lab.c_str(), lens_of(1 + (int)i));
+                        conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, lab.c_str(),
+                             lens_of(1 + (int)i));
                     }
                     if (last && sum_planes && !closes) fin.push_back(ptr(*dst));
                     if (last && n_streams > 1 && j + 1 < n_rb)
@@ -824,7 +847,8 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         h->prof_begin(st, "conv_post", 2.0 * h->post_cin * 7 * (double)B * Tw,
                       (double)B * Tw * (ESZ * h->post_cin + 4.0));
         tc_conv_post_tanh<P, 7><<<grid, kPostThreads, post_smem, st>>>(
-            ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride);
+            ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride,
+            lens_of((int)h->ups.size()), lens_of(1 + (int)h->ups.size()));
         h->prof_end(st);
         h->stage_end(st);
         check_cuda(cudaGetLastError(), "tc_conv_post_tanh launch");
@@ -865,12 +889,17 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
         if (which == 2)
             tc_launch_pair<P>(h, st, PL, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
                               (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
-                              nullptr, 0, B, T, "bench");
+                              nullptr, 0, nullptr, B, T, "bench");
         else
             tc_launch_conv<P>(h, st, a, B, L.cout, "bench", 0, 0);
     };
     for (int i = 0; i < 3; ++i) launch();
-    if (const char* tl_path = getenv("HFG_TC_TIMELINE")) {
+#ifdef HFG_TUNING
+    const char* tl_path_env = getenv("HFG_TC_TIMELINE");
+#else
+    const char* tl_path_env = nullptr;
+#endif
+    if (const char* tl_path = tl_path_env) {
         // tuning only: one extra launch with per-phase clock stamps of the first 4 CTAs, dumped as text
         const size_t n = 4 * 16 * 16;
         unsigned long long* d = nullptr;
@@ -905,12 +934,12 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
 }
 
 inline void tc_forward(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws, int mode,
-                       cudaStream_t st, float* const* stage_out) {
+                       cudaStream_t st, float* const* stage_out, const int* lengths = nullptr, int halo = 0) {
     if (h->cc_major != 10)
         throw StatusError(HFG_ERR_UNSUPPORTED, "tensor-core modes need an sm_100 device (tcgen05)");
-    if (mode == HFG_MODE_BF16) tc_forward_impl<PREC_BF16>(h, mel, B, T, wav, ws, st, stage_out);
-    else if (mode == HFG_MODE_FP16) tc_forward_impl<PREC_FP16>(h, mel, B, T, wav, ws, st, stage_out);
-    else tc_forward_impl<PREC_TF32>(h, mel, B, T, wav, ws, st, stage_out);
+    if (mode == HFG_MODE_BF16) tc_forward_impl<PREC_BF16>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
+    else if (mode == HFG_MODE_FP16) tc_forward_impl<PREC_FP16>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
+    else tc_forward_impl<PREC_TF32>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
 }
 
 inline void configure_kernels(hfg_handle*) {

@@ -81,13 +81,22 @@ tc_up_kernel(const TcUpArgs ua) {
     // work items of this CTA: item, item + gridDim.x, ...
     const int item0 = (int)blockIdx.x, item_step = (int)gridDim.x;
     auto taps_of = [&](int phase) { return a.phases > 1 ? (a.k - phase + a.u - 1) / a.u : a.taps_max; };
+    // variable-length batches (a.len_rows: OUTPUT rows utterance b needs, or null): an item whose tile starts at
+    // or beyond the last q position that utterance needs is skipped by every role alike
+    auto item_live = [&](int item) {
+        if (!a.len_rows) return true;
+        const int tile = item / ua.pn_per_tile;
+        const int q0 = (tile % a.tiles_per_batch) * MT * 128;
+        return q0 < tc_len_nq(a, a.len_rows[tile / a.tiles_per_batch]);
+    };
+    auto next_live = [&](int item) { while (item < ua.n_items && !item_live(item)) item += item_step; return item; };
 
     if (warp == 0) {
         // ===================== producer: two independent streams (activation K blocks, weight stages) =====================
         const bool leader = elect_one();
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
-        int a_item = item0, a_kb = 0;                       // next activation block
-        int w_item = item0, w_kb = 0, w_tap0 = 0;           // next weight stage
+        int a_item = next_live(item0), a_kb = 0;            // next activation block
+        int w_item = a_item, w_kb = 0, w_tap0 = 0;          // next weight stage
         uint32_t idle = 0;
         long long t_idle0 = 0;
         while (a_item < ua.n_items || w_item < ua.n_items) {
@@ -107,7 +116,7 @@ tc_up_kernel(const TcUpArgs ua) {
                 }
                 __syncwarp();
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
-                if (++a_kb == n_kb) { a_kb = 0; a_item += item_step; }
+                if (++a_kb == n_kb) { a_kb = 0; a_item = next_live(a_item + item_step); }
                 did = true;
             }
             if (w_item < ua.n_items && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
@@ -126,7 +135,7 @@ tc_up_kernel(const TcUpArgs ua) {
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                 w_tap0 += G;
-                if (w_tap0 >= taps) { w_tap0 = 0; if (++w_kb == n_kb) { w_kb = 0; w_item += item_step; } }
+                if (w_tap0 >= taps) { w_tap0 = 0; if (++w_kb == n_kb) { w_kb = 0; w_item = next_live(w_item + item_step); } }
                 did = true;
             }
             if (did) { idle = 0; t_idle0 = 0; continue; }
@@ -145,7 +154,7 @@ tc_up_kernel(const TcUpArgs ua) {
         const uint32_t a_lbo = ((uint32_t)R) << 16, b_lbo = ((uint32_t)N) << 16;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t it = 0;
-        for (int item = item0; item < ua.n_items; item += item_step, ++it) {
+        for (int item = next_live(item0); item < ua.n_items; item = next_live(item + item_step), ++it) {
             const int pn = item % ua.pn_per_tile;
             const int taps = taps_of(pn / ua.n_ctile);
             const uint32_t buf = it & 1u;
@@ -197,7 +206,7 @@ tc_up_kernel(const TcUpArgs ua) {
         const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         const int col_step = 32 * (n_epi_warps / 4);
         uint32_t it = 0;
-        for (int item = item0; item < ua.n_items; item += item_step, ++it) {
+        for (int item = next_live(item0); item < ua.n_items; item = next_live(item + item_step), ++it) {
             const int tile = item / ua.pn_per_tile, pn = item % ua.pn_per_tile;
             const int phase = pn / ua.n_ctile, ntile = pn % ua.n_ctile;
             const int b = tile / a.tiles_per_batch;

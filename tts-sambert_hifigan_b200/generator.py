@@ -236,41 +236,62 @@ class HiFiGANGenerator(nn.Module):
         the first kernel reads the frames-last layout directly."""
         if mel_pred.dim() != 3 or mel_pred.shape[2] != self.n_mels:
             raise RuntimeError(f"expected mel_pred of shape [B, Tfrm, {self.n_mels}], got {list(mel_pred.shape)}")
-        self._frames_last = True
-        try:
-            # shape checks / dispatch work on the logical [B, n_mels, T] view; the buffer stays [B, T, C]
-            return self.forward(mel_pred.contiguous().transpose(1, 2))
-        finally:
-            self._frames_last = False
+        # shape checks / dispatch work on the logical [B, n_mels, T] view; the buffer stays [B, T, C]
+        return self.forward(mel_pred.contiguous().transpose(1, 2), _frames_last=True)
+
+    @property
+    def receptive_radius(self) -> int:
+        """Mel frames on either side that one output frame depends on (13 for the default configuration),
+        derived from the kernel sizes / dilations / rates by the library (hfg_receptive_radius)."""
+        return _capi.receptive_radius(self._cfg)
 
     @torch.no_grad()
-    def forward_ragged(self, mel: torch.Tensor, lengths, halo: int = 14, bucket: int = 64) -> torch.Tensor:
-        """Variable-length batch: mel [B, n_mels, Tmax] zero- (or garbage-) padded, `lengths` the valid
-        frame counts.  The reference has no masks and synthesises every utterance out to the batch
-        maximum; here utterances are grouped by length and each group is generated
-        only up to its longest member + `halo` frames (the receptive radius is 13 frames, so the VALID
-        region [0, len*hop) of every utterance is bit-identical to the full-length run -- checked by
-        tests/test_parity_gpu.py::test_ragged_batch_valid_region_is_identical).  Samples beyond
-        (len + halo) * hop are returned as zeros instead of the reference's padding-driven garbage."""
+    def forward_ragged(self, mel: torch.Tensor, lengths, halo: Optional[int] = None) -> torch.Tensor:
+        """Variable-length batch: mel [B, n_mels, Tmax] padded with whatever the producer left there,
+        `lengths` the valid frame counts.  The reference has no masks and synthesises every utterance out to
+        the batch maximum (reference models/variance_adaptor.py:240-264); here the
+        kernels' tile schedulers skip every tile beyond (length + halo) frames (hfg_forward_lengths), in one
+        launch sequence for the whole batch.  Samples [0, len*hop) of every utterance are bit-identical to
+        forward(mel) of the same padded batch -- `halo` defaults to receptive_radius + 1 and smaller values are
+        rejected -- and everything beyond is returned as zeros."""
         self._check_input(mel)
-        lens = [int(x) for x in (lengths.tolist() if hasattr(lengths, "tolist") else lengths)]
+        if not mel.is_cuda:
+            raise RuntimeError("forward_ragged needs a CUDA mel (the length table is built on the device)")
         B, _, T = mel.shape
-        if len(lens) != B or min(lens) < 1 or max(lens) > T:
+        lens = torch.as_tensor(lengths)
+        if lens.numel() != B:
+            raise RuntimeError("lengths must hold one frame count per utterance")
+        if int(lens.min()) < 1 or int(lens.max()) > T:
             raise RuntimeError("lengths must hold one frame count in [1, Tmax] per utterance")
-        hop = self._stage_shapes(1, 1)[-1][2]
-        if self._stage_shapes(1, 2)[-1][2] != 2 * hop:
-            raise RuntimeError("forward_ragged needs T_out == T*hop (upsample kernels with even k-u)")
-        wav = torch.zeros((B, 1, T * hop), dtype=torch.float32, device=mel.device)
-        groups = {}
-        for i, n in enumerate(lens):
-            groups.setdefault(min(T, (n + halo + bucket - 1) // bucket * bucket), []).append(i)
-        for t_run, idx in sorted(groups.items()):
-            sel = torch.as_tensor(idx, device=mel.device)
-            out = self.forward(mel.index_select(0, sel)[:, :, :t_run].contiguous())
-            wav[sel, :, : t_run * hop] = out
+        radius = self.receptive_radius
+        halo = radius + 1 if halo is None else int(halo)
+        if halo < radius:
+            raise ValueError(f"halo={halo} is smaller than the receptive radius ({radius} frames) of this "
+                             "configuration: the valid region would not match the full-length run")
+        dev = mel.device
+        lens_dev = lens.to(device=dev, dtype=torch.int32).contiguous()
+        shapes = self._stage_shapes(B, T)
+        mode = _capi.MODES[self.mode]
+        buf = mel.contiguous()
+        with torch.cuda.device(dev):
+            h = self._handle_for(dev)
+            h.set_mel_layout(False)
+            ws = self._workspace(h, dev, B, T, mode)
+            wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32, device=dev)
+            h.forward_lengths(buf.data_ptr(), lens_dev.data_ptr(), halo, B, T, wav.data_ptr(), ws.data_ptr(),
+                              ws.numel(), mode, torch.cuda.current_stream(dev).cuda_stream)
+            self.last_launch_count = h.last_launch_count()
         return wav
 
-    def forward(self, mel: torch.Tensor, _stages: Optional[list] = None) -> torch.Tensor:
+    def _workspace(self, h, dev, B, T, mode):
+        need = h.workspace_bytes(B, T, mode)
+        ws = self._workspaces.get(dev.index)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._workspaces[dev.index] = ws
+        return ws
+
+    def forward(self, mel: torch.Tensor, _stages: Optional[list] = None, _frames_last: bool = False) -> torch.Tensor:
         """Generate waveform from mel-spectrogram (reference models/hifigan.py:224-261).
 
         CUDA mel: runs asynchronously on the current stream, returns a CUDA tensor.
@@ -278,8 +299,6 @@ class HiFiGANGenerator(nn.Module):
         (hfg_forward_host); returns a CPU tensor.  Without a CUDA device this
         raises -- there is no CPU implementation."""
         self._check_input(mel)
-        if not torch.cuda.is_available():
-            raise RuntimeError("HiFiGANGenerator (B200) needs a CUDA device: there is no CPU fallback")
         B, _, T = mel.shape
         shapes = self._stage_shapes(B, T)
         if self.debug_shapes:
@@ -289,7 +308,7 @@ class HiFiGANGenerator(nn.Module):
                 print(f"[HiFiGANGenerator] After upsample {i}: {torch.Size(shapes[i + 1])}")
                 print(f"[HiFiGANGenerator] After MRF {i}: {torch.Size(shapes[i + 1])}")
         try:
-            wav = self._dispatch(mel, shapes, _capi.MODES[self.mode], _stages)
+            wav = self._dispatch(mel, shapes, _capi.MODES[self.mode], _stages, _frames_last)
         except _capi.HfgError as e:
             # geometry the UMMA shapes do not cover (channel counts not multiples of 16): the fp32
             # CUDA kernels handle any geometry.  Still the GPU -- there is no CPU path.
@@ -300,32 +319,30 @@ class HiFiGANGenerator(nn.Module):
             self.mode = "fp32"
             if _stages is not None:
                 _stages.clear()
-            wav = self._dispatch(mel, shapes, _capi.MODES["fp32"], _stages)
+            wav = self._dispatch(mel, shapes, _capi.MODES["fp32"], _stages, _frames_last)
         if self.debug_shapes:
             print(f"[HiFiGANGenerator] Output wav shape: {wav.shape}")
         return wav
 
-    def _dispatch(self, mel, shapes, mode, stages):
-        if getattr(self, "_frames_last", False):
+    def _dispatch(self, mel, shapes, mode, stages, frames_last):
+        if not torch.cuda.is_available():
+            raise RuntimeError("HiFiGANGenerator (B200) needs a CUDA device: there is no CPU fallback")
+        if frames_last:
             buf = mel.transpose(1, 2)                   # back to the caller's contiguous [B, T, C] buffer
             assert buf.is_contiguous()
         else:
             buf = mel.contiguous()
         if mel.is_cuda:
-            return self._forward_cuda(buf, shapes, mode, stages, mel.shape)
-        return self._forward_host(buf, shapes, mode, mel.shape)
+            return self._forward_cuda(buf, shapes, mode, stages, mel.shape, frames_last)
+        return self._forward_host(buf, shapes, mode, mel.shape, frames_last)
 
-    def _forward_cuda(self, mel, shapes, mode, stages, logical_shape):
+    def _forward_cuda(self, mel, shapes, mode, stages, logical_shape, frames_last):
         dev = mel.device
         B, _, T = logical_shape
         with torch.cuda.device(dev):
             h = self._handle_for(dev)
-            h.set_mel_layout(getattr(self, "_frames_last", False))
-            need = h.workspace_bytes(B, T, mode)
-            ws = self._workspaces.get(dev.index)
-            if ws is None or ws.numel() < need:
-                ws = torch.empty(need, dtype=torch.uint8, device=dev)
-                self._workspaces[dev.index] = ws
+            h.set_mel_layout(frames_last)
+            ws = self._workspace(h, dev, B, T, mode)
             wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32, device=dev)
             stage_ptrs = None
             if stages is not None:
@@ -338,11 +355,11 @@ class HiFiGANGenerator(nn.Module):
             self.last_launch_count = h.last_launch_count()
         return wav
 
-    def _forward_host(self, mel, shapes, mode, logical_shape):
+    def _forward_host(self, mel, shapes, mode, logical_shape, frames_last):
         dev = torch.device("cuda", torch.cuda.current_device())
         B, _, T = logical_shape
         h = self._handle_for(dev)
-        h.set_mel_layout(getattr(self, "_frames_last", False))
+        h.set_mel_layout(frames_last)
         # the result is written by DMA straight into a page-locked tensor (torch caches these)
         wav = torch.empty((B, 1, shapes[-1][2]), dtype=torch.float32, pin_memory=True)
         h.forward_host(mel.data_ptr(), B, T, wav.data_ptr(), mode,

@@ -23,7 +23,21 @@ from typing import Callable, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-RECEPTIVE_HALO_FRAMES = 14      # exact receptive radius is 13 frames for the default config
+RECEPTIVE_HALO_FRAMES = 14      # default configuration: exact receptive radius 13 frames, + 1
+
+
+def resolve_halo(generate, halo: Optional[int]) -> int:
+    """Halo in frames for `generate`.  A generator that knows its own geometry (HiFiGANGenerator.receptive_radius,
+    derived from kernel sizes / dilations / rates) supplies radius + 1 as the default and rejects anything
+    smaller than the radius -- a too-small halo silently changes the output near chunk borders.  A plain callable
+    (the CPU oracle in the gloo tests) gets the default configuration's 14."""
+    owner = getattr(generate, "__self__", generate)
+    radius = getattr(owner, "receptive_radius", None)
+    if halo is None:
+        return RECEPTIVE_HALO_FRAMES if radius is None else int(radius) + 1
+    if radius is not None and halo < int(radius):
+        raise ValueError(f"halo={halo} frames is smaller than the receptive radius {int(radius)} of this generator")
+    return int(halo)
 
 
 def shard_bounds(n_items: int, world: int, rank: int) -> Tuple[int, int]:
@@ -74,8 +88,9 @@ def run_chunk(generate: Callable[[torch.Tensor], torch.Tensor], mel: torch.Tenso
 
 
 def generate_chunked(generate, mel: torch.Tensor, n_chunks: int, hop: int = 256,
-                     halo: int = RECEPTIVE_HALO_FRAMES) -> torch.Tensor:
+                     halo: Optional[int] = None) -> torch.Tensor:
     """Single-process time chunking (bounded memory for long-form input)."""
+    halo = resolve_halo(generate, halo)
     parts = [run_chunk(generate, mel, c, hop) for c in plan_chunks(mel.shape[-1], n_chunks, halo)]
     return torch.cat(parts, dim=-1)
 
@@ -127,10 +142,11 @@ def generate_utterance_sharded(generate, mel: torch.Tensor, group=None, gather: 
     return _gather_var(local, sizes, 0, group, dst)
 
 
-def generate_time_sharded(generate, mel: torch.Tensor, hop: int = 256, halo: int = RECEPTIVE_HALO_FRAMES,
+def generate_time_sharded(generate, mel: torch.Tensor, hop: int = 256, halo: Optional[int] = None,
                           group=None, gather: bool = True, dst: Optional[int] = None) -> Optional[torch.Tensor]:
     """Long-form input: rank r generates frame range shard_bounds(T, world, r)
     from its mel slice with halo, then the cropped pieces are gathered along time."""
+    halo = resolve_halo(generate, halo)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     T = mel.shape[-1]
     a, b = shard_bounds(T, world, rank)
