@@ -816,8 +816,9 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                                           lens_of(1 + (int)i), B, S.X.T, lab.c_str());
                     } else {
                         // unfused fallback: conv1 -> scratch, conv2 (+ residual) -> dst
-                        conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, lab.c_str(), lens_of(1 + (int)i));
-                        conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, lab.c_str(),
+                        const std::string clab = lab + ":conv";       // profile label of the unfused launches
+                        conv(sj, rb[l].c1, *r, &W.S, nullptr, nullptr, TC_ACC_NONE, clab.c_str(), lens_of(1 + (int)i));
+                        conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, clab.c_str(),
                              lens_of(1 + (int)i));
                     }
                     if (last && sum_planes && !closes) fin.push_back(ptr(*dst));
