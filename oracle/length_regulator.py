@@ -6,8 +6,11 @@ import numpy as np
 
 
 def durations_from_log(log_dur: np.ndarray) -> np.ndarray:
-    # torch.exp(x).round().long() then clamp(min=1); torch.round is half-to-even == np.rint
-    d = np.rint(np.exp(log_dur.astype(np.float32))).astype(np.int64)
+    # torch.exp(x).round().long() then clamp(min=1); torch.round is half-to-even == np.rint.  exp is taken in
+    # float64 and rounded to float32 once (the correctly rounded float32 exponential the reference's float32
+    # tensor approximates to within 1 ulp); tests/test_length_regulator.py counts where the live reference's
+    # CPU vector expf lands on the other side of a tie.
+    d = np.rint(np.exp(log_dur.astype(np.float64)).astype(np.float32)).astype(np.int64)
     return np.maximum(d, 1)
 
 

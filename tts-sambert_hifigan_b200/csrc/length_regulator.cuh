@@ -8,11 +8,16 @@
 
 namespace hfg {
 
-// dur = max(1, (long) rint(exp(log_dur)))   -- torch.round is round-half-to-even == rintf
+// dur = max(1, (long) rint(exp(log_dur)))   -- torch.round is round-half-to-even == rintf.
+// The reference materialises exp() as a float32 tensor before rounding (models/variance_adaptor.py:746), so the
+// result is DEFINED here as rintf of the correctly rounded float32 exponential: exp is evaluated in fp64 (error
+// < 1 fp64 ulp, far below half an fp32 ulp except in astronomically rare double-rounding cases) and rounded to
+// fp32 once.  Deterministic, independent of the device's fast-math expf, and closest to the true value; a CPU
+// vector expf that is 1 ulp off can disagree only where exp(x) lies within 1 fp32 ulp of k + 0.5.
 __global__ void lr_durations_from_log(const float* __restrict__ log_dur, long long n, long long* __restrict__ dur) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float d = rintf(expf(log_dur[i]));
+    const float d = rintf((float)exp((double)log_dur[i]));
     const long long v = (long long)d;
     dur[i] = v < 1 ? 1 : v;
 }
