@@ -37,7 +37,7 @@ constexpr int kPairMaxSA = 6;                     // activation ring slots (K bl
 struct TcPairArgs {
     const uint8_t* a; long long a_bstride, a_pstride;     // leaky_relu(x) planes
     const uint8_t* w1; const uint8_t* w2;                 // packed [kb][tap][chunk][N][16 B]; CTA pair: [half][..][N/2][16 B]
-    long long w_half_stride;                              // bytes between the two N-halves (CTA pair only)
+    long long w_half_stride, w2_half_stride;              // bytes between the two N-halves (CTA pair only)
     const float* b1; const float* b2;
     uint8_t* out; long long o_bstride, o_pstride;         // leaky_relu(x_new) planes (may be null)
     float* acc; long long acc_bstride, acc_pstride;       // MRF fp32 partial sums (bytes): unfused-neighbour fallback only
@@ -90,17 +90,22 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// P2 = operand precision of conv2, i.e. of the on-chip intermediate H and of W2.  P2 == P except in tf32 mode,
+// where P2 = PREC_FP16: the MMA would round the fp32 H tile to tf32's 10-bit mantissa anyway, so the epilogue
+// stores it as fp16 (same mantissa, round-to-nearest, saturating) -- conv2 then runs at the fp16 MMA rate on
+// half the shared-memory operand bytes, and the H tile of C = 256 fits next to the operand rings.  The
+// residual stream (A tile -> acc2 -> output planes) stays fp32.
 // MINB = CTAs per SM the register allocation must allow (2 for the narrow layers, whose tiles are
 // latency-bound and want a second CTA to fill the tensor pipe while the first one is in an epilogue)
 // CTAS = 2: a cluster of two CTAs runs two adjacent tiles in lockstep; the leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256) for both, each CTA stages only its half of every weight tile
 // (half the L2->smem weight traffic and half the B-operand smem reads per SM).
-template <int P, int MINB, int CTAS>
+template <int P, int P2, int MINB, int CTAS>
 __global__ void __launch_bounds__(kPairThreads, MINB)
 tc_pair_kernel(const TcPairArgs a) {
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
     uint8_t* smem = tc_pair_smem;
-    constexpr int CW = Prec<P>::CW;
+    constexpr int CW = Prec<P>::CW, CW2 = Prec<P2>::CW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = a.N, MT = a.MT, R1 = a.R1, RH = a.RH, k = a.k;
@@ -110,13 +115,15 @@ tc_pair_kernel(const TcPairArgs a) {
     const int KBC = a.kbc;                            // 16-byte cells per K block (8, or 4 when smem is tight)
     const int nck_max = n_chunks < KBC ? n_chunks : KBC;
     const int n_kb = (n_chunks + KBC - 1) / KBC;
+    const int n_chunks2 = N / CW2;                    // cells per row of the H tile (conv2's K extent)
+    const int n_kb2 = (n_chunks2 + KBC - 1) / KBC;
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
     const int G = a.tap_group;
     const uint32_t w_stage_bytes = (uint32_t)G * NB * nck_max * 16;
     uint8_t* sA = smem;
     uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
     uint8_t* sH = sW + (size_t)a.sw * w_stage_bytes;
-    float* sB1 = reinterpret_cast<float*>(sH + (size_t)n_chunks * RH * 16);
+    float* sB1 = reinterpret_cast<float*>(sH + (size_t)n_chunks2 * RH * 16);
     float* sB2 = sB1 + N;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + N);
     const uint32_t bar0 = smem_u32(bars);
@@ -224,7 +231,8 @@ tc_pair_kernel(const TcPairArgs a) {
                 did = true;
             }
             if (w_sc < n_sched && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
-                const int nck = (n_chunks - KBC * w_kb) < KBC ? (n_chunks - KBC * w_kb) : KBC;
+                const int w_chunks = w_conv ? n_chunks2 : n_chunks, w_nkb = w_conv ? n_kb2 : n_kb;
+                const int nck = (w_chunks - KBC * w_kb) < KBC ? (w_chunks - KBC * w_kb) : KBC;
                 const int tap0 = w_g * G;
                 const int g = (k - tap0) < G ? (k - tap0) : G;
                 if (w_conv == 0 && w_kb == 0 && w_g == 0) HFG_TL(11, w_t);
@@ -233,13 +241,13 @@ tc_pair_kernel(const TcPairArgs a) {
                     const uint8_t* w = w_conv ? a.w2 : a.w1;
                     mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
-                             w + (long long)rank * a.w_half_stride +
+                             w + (long long)rank * (w_conv ? a.w2_half_stride : a.w_half_stride) +
                                  ((long long)w_kb * k * KBC + (long long)tap0 * nck) * NB * 16,
                              (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
                 }
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                if (++w_g == groups) { w_g = 0; if (++w_kb == n_kb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
+                if (++w_g == groups) { w_g = 0; if (++w_kb == w_nkb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
                 did = true;
             }
             if (did) { idle = 0; t_idle0 = 0; continue; }
@@ -253,7 +261,7 @@ tc_pair_kernel(const TcPairArgs a) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<P>(N, 128 * CTAS);
+        const uint32_t idesc = umma_idesc<P>(N, 128 * CTAS), idesc2 = umma_idesc<P2>(N, 128 * CTAS);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
         const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)NB) << 16;
         auto commit = [&](uint32_t bar) { if constexpr (CTAS == 2) tc_commit2(bar); else tc_commit(bar); };
@@ -262,7 +270,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // slot, so slots are forwarded independently instead of through one serial wait chain ----
             int n_my = 0;
             for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step)) ++n_my;
-            const int stages_per_tile = 2 * n_kb * ((k + G - 1) / G);
+            const int stages_per_tile = (n_kb + n_kb2) * ((k + G - 1) / G);
             const int total_w = n_my * stages_per_tile, total_a = n_my * n_kb;
             if (lane < a.sw) {
                 const int uses = total_w / a.sw + (lane < total_w % a.sw ? 1 : 0);
@@ -324,8 +332,8 @@ tc_pair_kernel(const TcPairArgs a) {
             if constexpr (CTAS == 2) mbar_wait_cluster(H_READY, it & 1); else mbar_wait(H_READY, it & 1);
             tc_fence_after();
             HFG_TL(3, it);
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
+            for (int kb = 0; kb < n_kb2; ++kb) {
+                const int nck = (n_chunks2 - KBC * kb) < KBC ? (n_chunks2 - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
                 const uint32_t h_lo0 = h_lo_base + (uint32_t)(KBC * kb * RH);
                 for (int tap0 = 0; tap0 < k; tap0 += G) {
@@ -338,8 +346,8 @@ tc_pair_kernel(const TcPairArgs a) {
                             const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
                             const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : 1));
                             for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<P, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc, ksteps, 1u);
+                                umma_ksteps<P2, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc2, ksteps, 1u);
                         }
                         commit(W_EMPTY(sw_i));
                     }
@@ -446,14 +454,14 @@ tc_pair_kernel(const TcPairArgs a) {
                     add_bias16(v, sB1 + c0);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
-                    store_cells16<P>(hp + (long long)(c0 / CW) * h_plane, h_plane, v);
+                    store_cells16<P2>(hp + (long long)(c0 / CW2) * h_plane, h_plane, v);
                     if (two) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r1[i]);
                         add_bias16(v, sB1 + c0 + 16);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = drop ? 0.f : lrelu(v[i], slope);
-                        store_cells16<P>(hp + (long long)((c0 + 16) / CW) * h_plane, h_plane, v);
+                        store_cells16<P2>(hp + (long long)((c0 + 16) / CW2) * h_plane, h_plane, v);
                     }
                 }
             }

@@ -435,8 +435,15 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
     return true;
 }
 
+// Operand precision of conv2 inside the fused pair (tc_pair_kernel.cuh): the on-chip intermediate of the tf32
+// mode is held as fp16 -- tf32's own 10-bit mantissa -- which halves its shared-memory footprint and operand
+// reads and runs conv2 at the fp16 MMA rate.
+static inline int tc_pair_p2(int prec) {
+    return (prec == PREC_TF32 && env_int("HFG_TC_TF32_H16", 1)) ? PREC_FP16 : prec;
+}
+
 static inline int tc_pair_ctas(const PairLayers& P, int prec) {
-    const bool bf16 = prec != PREC_TF32;                               // 2-byte operands (bf16 or fp16)
+    const bool bf16 = prec != PREC_TF32 || tc_pair_p2(prec) != PREC_TF32;   // 2-byte H tile: the pair fits for every C
     // CTA pairs (cta_group::2: half the weight staging and B-operand reads per SM) where measured faster
     // (profiles/r1_tuning.md sections 5 and 7): every C >= 64 layer, except tf32 C = 256 whose fp32 H tile
     // leaves too little shared memory (the fused pair measured slower than two unfused launches there).
@@ -444,7 +451,7 @@ static inline int tc_pair_ctas(const PairLayers& P, int prec) {
     const int N = P.c1.cout;
     const int dflt = (N >= 64 && (bf16 || N <= 128)) ? 2 : 1;
     const int want = env_int("HFG_TC_PAIR_CTAS", dflt);
-    return (want == 2 && P.c1.tc.w_pair[prec][1][0] && P.c2.tc.w_pair[prec][1][0]) ? 2 : 1;
+    return (want == 2 && P.c1.tc.w_pair[prec][1][0] && P.c2.tc.w_pair[tc_pair_p2(prec)][1][0]) ? 2 : 1;
 }
 
 static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, int prec) {
@@ -456,6 +463,8 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     if (P.c2.dil != 1 || p1 + p2 > kPadL || 2 * p2 >= 128 || p2 > p1) return g;
     const int mt_cap = env_int("HFG_TC_PAIR_MT", 4);
     const int ctas = tc_pair_ctas(P, prec);
+    const int prec2 = tc_pair_p2(prec);
+    const int n_chunks2 = N / (prec2 == PREC_TF32 ? 4 : 8);               // cells per row of the H tile
     const int NB = N / ctas;                                              // weight rows staged per CTA
     // Candidates from the largest tile down.  Measured rule (profiles/r1_tuning.md): two co-resident
     // CTAs per SM beat one CTA with a larger tile (one CTA's epilogue hides behind the other's MMAs),
@@ -466,7 +475,7 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     for (int MT : {4, 2, 1}) {
         if (MT > mt_cap || 2 * MT * N > 512) continue;
       for (int kbc : {8, 4}) {
-        if (!P.c1.tc.w_pair[prec][ctas - 1][kbc == 4 ? 1 : 0]) continue;
+        if (!P.c1.tc.w_pair[prec][ctas - 1][kbc == 4 ? 1 : 0] || !P.c2.tc.w_pair[prec2][ctas - 1][kbc == 4 ? 1 : 0]) continue;
         if (kbc == 4 && env_int("HFG_TC_PAIR_NO_KBC4", 0)) continue;
         const int nck_max = std::min(kbc, n_chunks), n_kb = (n_chunks + kbc - 1) / kbc;
         // W ring.  Measured (profiles/r1_tuning.md section 6): with the data always ready the kernel is still
@@ -479,7 +488,7 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
         const size_t tap_bytes = (size_t)NB * nck_max * 16;
         const size_t a_stage = (size_t)R1 * nck_max * 16;
-        const size_t fixed0 = (size_t)n_chunks * RH * 16 + (size_t)2 * N * 4 + (size_t)env_int("HFG_TC_PAIR_PAD", 512);
+        const size_t fixed0 = (size_t)n_chunks2 * RH * 16 + (size_t)2 * N * 4 + (size_t)env_int("HFG_TC_PAIR_PAD", 512);
         int ncols = 32;
         while (ncols < 2 * MT * N) ncols <<= 1;
         const int sw_min = std::max(2, env_int("HFG_TC_PAIR_SWMIN", 2));
@@ -543,9 +552,11 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     TcPairArgs a{};
     a.a = in; a.a_bstride = in_b; a.a_pstride = in_p;
     const int vk = g.kbc == 4 ? 1 : 0;
+    const int P2 = tc_pair_p2(P);
     a.w1 = reinterpret_cast<const uint8_t*>(L.c1.tc.w_pair[P][g.ctas - 1][vk]);
-    a.w2 = reinterpret_cast<const uint8_t*>(L.c2.tc.w_pair[P][g.ctas - 1][vk]);
+    a.w2 = reinterpret_cast<const uint8_t*>(L.c2.tc.w_pair[P2][g.ctas - 1][vk]);
     a.w_half_stride = L.c1.tc.half_stride[P][vk];
+    a.w2_half_stride = L.c2.tc.half_stride[P2][vk];
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.dbg = env_int("HFG_TC_DBG", 0);
@@ -567,10 +578,15 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     const int ctas = g.ctas;
     using KernelFn = void (*)(TcPairArgs);
     KernelFn fn = nullptr;
-    if (ctas == 2) fn = two ? tc_pair_kernel<P, 2, 2> : tc_pair_kernel<P, 1, 2>;
-    else fn = two ? tc_pair_kernel<P, 2, 1> : tc_pair_kernel<P, 1, 1>;
+    if (P == PREC_TF32 && P2 == PREC_FP16) {
+        if (ctas == 2) fn = two ? tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 2> : tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 2>;
+        else fn = two ? tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 1> : tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 1>;
+    } else {
+        if (ctas == 2) fn = two ? tc_pair_kernel<P, P, 2, 2> : tc_pair_kernel<P, P, 1, 2>;
+        else fn = two ? tc_pair_kernel<P, P, 2, 1> : tc_pair_kernel<P, P, 1, 1>;
+    }
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
-    int& regs = h->pair_regs[P][two ? 1 : 0][ctas - 1];
+    int& regs = h->pair_regs[P == PREC_TF32 && P2 == PREC_FP16 ? 3 : P][two ? 1 : 0][ctas - 1];
     if (regs == 0) {
         cudaFuncAttributes fa{};
         check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
@@ -954,9 +970,11 @@ inline void configure_kernels(hfg_handle*) {
     auto each = [&](auto prec) {
         constexpr int P = decltype(prec)::value;
         big(tc_conv_kernel<P>); big(tc_up_kernel<P>);
-        big(tc_pair_kernel<P, 1, 1>); big(tc_pair_kernel<P, 2, 1>);
-        big(tc_pair_kernel<P, 1, 2>); big(tc_pair_kernel<P, 2, 2>);
+        big(tc_pair_kernel<P, P, 1, 1>); big(tc_pair_kernel<P, P, 2, 1>);
+        big(tc_pair_kernel<P, P, 1, 2>); big(tc_pair_kernel<P, P, 2, 2>);
     };
+    big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 1>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 1>);
+    big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 2>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 2>);
     each(std::integral_constant<int, PREC_TF32>{});
     each(std::integral_constant<int, PREC_BF16>{});
     each(std::integral_constant<int, PREC_FP16>{});
