@@ -6,5 +6,6 @@ from . import synth  # noqa: F401
 from . import _capi  # noqa: F401
 from .generator import HiFiGANGenerator  # noqa: F401
 from .length_regulator import LengthRegulator, durations_from_log  # noqa: F401
+from .ar_decoder import PNCAARDecoder  # noqa: F401
 
-__all__ = ["HiFiGANGenerator", "LengthRegulator", "durations_from_log", "synth"]
+__all__ = ["HiFiGANGenerator", "LengthRegulator", "PNCAARDecoder", "durations_from_log", "synth"]

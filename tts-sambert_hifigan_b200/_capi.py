@@ -21,6 +21,11 @@ SYMBOLS = [
     "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
     "hfg_forward_lengths", "hfg_receptive_radius",
 ]
+# include/hfg_ard.h (KV-cached autoregressive decoder)
+ARD_SYMBOLS = [
+    "hfg_ard_create", "hfg_ard_destroy", "hfg_ard_last_error", "hfg_ard_set_weight", "hfg_ard_commit_weights",
+    "hfg_ard_workspace_bytes", "hfg_ard_decode", "hfg_ard_last_launch_count",
+]
 
 
 class HfgConfig(ctypes.Structure):
@@ -108,6 +113,22 @@ def load():
     lib.hfg_forward_lengths.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, ctypes.c_size_t, i32, vp]
     lib.hfg_receptive_radius.restype = ctypes.c_int
     lib.hfg_receptive_radius.argtypes = [ctypes.POINTER(HfgConfig), ctypes.POINTER(ctypes.c_int32)]
+    lib.hfg_ard_create.restype = ctypes.c_int
+    lib.hfg_ard_create.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.hfg_ard_destroy.restype = None
+    lib.hfg_ard_destroy.argtypes = [vp]
+    lib.hfg_ard_last_error.restype = ctypes.c_char_p
+    lib.hfg_ard_last_error.argtypes = [vp]
+    lib.hfg_ard_set_weight.restype = ctypes.c_int
+    lib.hfg_ard_set_weight.argtypes = [vp, ctypes.c_char_p, vp, i64p, i32]
+    lib.hfg_ard_commit_weights.restype = ctypes.c_int
+    lib.hfg_ard_commit_weights.argtypes = [vp]
+    lib.hfg_ard_workspace_bytes.restype = ctypes.c_int
+    lib.hfg_ard_workspace_bytes.argtypes = [vp, i32, i32, i32, ctypes.POINTER(ctypes.c_size_t)]
+    lib.hfg_ard_decode.restype = ctypes.c_int
+    lib.hfg_ard_decode.argtypes = [vp, vp, i32, i32, i32, vp, vp, ctypes.c_size_t, vp]
+    lib.hfg_ard_last_launch_count.restype = ctypes.c_int
+    lib.hfg_ard_last_launch_count.argtypes = [vp, i64p]
     lib.hfg_bench_layer.restype = ctypes.c_int
     lib.hfg_bench_layer.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, fp]
     del fp

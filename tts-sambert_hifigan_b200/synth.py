@@ -171,3 +171,42 @@ def make_weightnorm_weights(cfg: dict, seed: int) -> Dict[str, np.ndarray]:
         scale = uniform(seed, out[k].shape, 0.25, stream=1000 + i) + np.float32(1.0)
         out[k] = (out[k] * scale).astype(np.float32)
     return out
+
+
+# ---------------------------------------------------------------------------
+# autoregressive decoder (reference models/ar_decoder.py): portable weights
+# ---------------------------------------------------------------------------
+ARD_DEFAULT = dict(d_model=256, n_mels=80, n_layers=6, n_heads=8, d_ff=2048)
+
+
+def ard_weight_shapes(cfg: dict) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Parameter keys / shapes of the reference PNCAARDecoder's state_dict, in its order, without the
+    `pos_encoding.pe` buffer (which the module computes itself)."""
+    d, m, ff = cfg["d_model"], cfg["n_mels"], cfg["d_ff"]
+    out = [("prenet.0.weight", (d, m)), ("prenet.0.bias", (d,)), ("prenet.3.weight", (d, d)), ("prenet.3.bias", (d,))]
+    for i in range(cfg["n_layers"]):
+        L = f"decoder.layers.{i}."
+        for a in ("self_attn.", "multihead_attn."):
+            out += [(L + a + "in_proj_weight", (3 * d, d)), (L + a + "in_proj_bias", (3 * d,)),
+                    (L + a + "out_proj.weight", (d, d)), (L + a + "out_proj.bias", (d,))]
+        out += [(L + "linear1.weight", (ff, d)), (L + "linear1.bias", (ff,)),
+                (L + "linear2.weight", (d, ff)), (L + "linear2.bias", (d,))]
+        for n in ("norm1.", "norm2.", "norm3."):
+            out += [(L + n + "weight", (d,)), (L + n + "bias", (d,))]
+    out += [("mel_proj.weight", (m, d)), ("mel_proj.bias", (m,))]
+    return out
+
+
+def make_ard_weights(cfg: dict, seed: int) -> Dict[str, np.ndarray]:
+    """Xavier-uniform matrices (the reference's own init, models/ar_decoder.py:91-95), small non-zero biases and
+    LayerNorm gains around 1 -- from the portable generator, so both boxes build the same decoder."""
+    sd = {}
+    for idx, (name, shape) in enumerate(ard_weight_shapes(cfg)):
+        if len(shape) == 2:
+            bound = float(np.sqrt(6.0 / (shape[0] + shape[1])))
+            sd[name] = uniform(seed, shape, bound, stream=idx + 1)
+        elif ".norm" in name and name.endswith("weight"):
+            sd[name] = (1.0 + uniform(seed, shape, 0.1, stream=idx + 1)).astype(np.float32)
+        else:
+            sd[name] = uniform(seed, shape, 0.05, stream=idx + 1)
+    return sd
