@@ -21,6 +21,8 @@ SYMBOLS = [
     "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
     "hfg_forward_lengths", "hfg_receptive_radius",
 ]
+# include/hfg_mel.h (on-device log-mel / log-mel L1)
+MEL_SYMBOLS = ["hfg_mel_create", "hfg_mel_destroy", "hfg_mel_last_error", "hfg_mel_frames", "hfg_log_mel", "hfg_log_mel_l1"]
 # include/hfg_ard.h (KV-cached autoregressive decoder)
 ARD_SYMBOLS = [
     "hfg_ard_create", "hfg_ard_destroy", "hfg_ard_last_error", "hfg_ard_set_weight", "hfg_ard_commit_weights",
@@ -113,6 +115,18 @@ def load():
     lib.hfg_forward_lengths.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, ctypes.c_size_t, i32, vp]
     lib.hfg_receptive_radius.restype = ctypes.c_int
     lib.hfg_receptive_radius.argtypes = [ctypes.POINTER(HfgConfig), ctypes.POINTER(ctypes.c_int32)]
+    lib.hfg_mel_create.restype = ctypes.c_int
+    lib.hfg_mel_create.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.hfg_mel_destroy.restype = None
+    lib.hfg_mel_destroy.argtypes = [vp]
+    lib.hfg_mel_last_error.restype = ctypes.c_char_p
+    lib.hfg_mel_last_error.argtypes = [vp]
+    lib.hfg_mel_frames.restype = ctypes.c_int
+    lib.hfg_mel_frames.argtypes = [vp, ctypes.c_int64, i64p]
+    lib.hfg_log_mel.restype = ctypes.c_int
+    lib.hfg_log_mel.argtypes = [vp, vp, i32, ctypes.c_int64, vp, vp]
+    lib.hfg_log_mel_l1.restype = ctypes.c_int
+    lib.hfg_log_mel_l1.argtypes = [vp, vp, vp, i32, ctypes.c_int64, vp, vp, vp]
     lib.hfg_ard_create.restype = ctypes.c_int
     lib.hfg_ard_create.argtypes = [vp, ctypes.POINTER(vp)]
     lib.hfg_ard_destroy.restype = None
