@@ -7,7 +7,9 @@ generator hot path on N B200s (BASELINE.json metric).
     python bench.py --impl reference ...      # the CPU arm: reference path on host cores
 
 Headline line (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE.json configs[1] -- a step is one
-generator forward over 16 utterances x 172 frames (2 s each at 22.05 kHz, hop 256) in tf32 mode; every rank
+generator forward over 16 utterances x 172 frames (2 s each at 22.05 kHz, hop 256) in tf32 mode (fp32 activations
+in HBM, kind::tf32 MMAs; the on-chip intermediate of a fused ResBlock pair is held as fp16 = tf32's own 10-bit
+mantissa); every rank
 runs its own batch (utterance sharding, no data-path collective): "scaling": "weak".
 
   value  device-timed (CUDA events around each step, L2 flushed between steps, mel already resident in
@@ -531,6 +533,14 @@ def main():
                         "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma, "traffic": None,
                         "peak_source": "nominal fp32 FFMA rate 148 SM x 128 lanes x 2 x 1.965 GHz (not a tensor peak)"}
             dom = max(mrf, key=lambda p: p["ms"])
+            if mode == "tf32" and not dom["kernel"].endswith(":conv"):
+                # a fused pair in tf32 mode runs conv1 as kind::tf32 and conv2 on the fp16 copy of the on-chip
+                # intermediate (kind::f16): half of its FLOPs at each rate -> the peak of the launch is the
+                # harmonic mean of the two measured peaks
+                f16_b, f16_s = peaks["bf16_tflops"], peaks["bf16_tflops_sustained"]
+                burst, sustained = 2.0 / (1.0 / burst + 1.0 / f16_b), 2.0 / (1.0 / sustained + 1.0 / f16_s)
+                note += ("; fused pair = conv1 at the tf32 rate + conv2 at the fp16 rate (fp16 intermediate), equal "
+                         "FLOPs each: peak = harmonic mean of the tf32 and the bf16/fp16 burst peaks")
             achieved = dom["flops"] / (dom["ms"] / 1e3) / 1e12
             mrf_ms = sum(p["ms"] for p in mrf)
             mrf_tflops = sum(p["flops"] for p in mrf) / (mrf_ms / 1e3) / 1e12

@@ -726,27 +726,33 @@ __global__ void tc_mask_tail(float* __restrict__ y, const int* __restrict__ vali
 
 // conv_post (C_out = 1, K taps) + tanh from chunk planes that already hold leaky_relu(x)
 // (reference models/hifigan.py:254-256).  HBM-bound: reads C channels per step, writes one sample.
-// A block stages (kPostTile + K - 1) rows x C/CW cells in shared memory with coalesced 16-byte loads (each
-// cell is read from global once instead of K times); every thread then produces kPostR consecutive samples
-// from a sliding window: a cell is converted once and feeds up to kPostR * CW FMAs, a chunk's K * CW weights
-// are loaded once per thread.  (The one-sample-per-thread version issued ~700 instructions per sample and
-// ran at 22-26 % of the HBM roofline.)  Accumulation order per sample is chunk -> tap -> channel, as before.
+//
+// A block stages (kPostTile + K - 1) rows of up to kPostGC chunk columns in shared memory with 16-byte cp.async
+// copies (no register round trip, every copy of the block in flight at once: the first version of this kernel
+// spent its time in long-scoreboard stalls of a load -> store staging loop), then every thread produces
+// kPostR CONSECUTIVE samples from a sliding window: a cell is converted once and feeds up to kPostR * CW FMAs,
+// a chunk's K * CW weights are loaded once per thread.  Threads of a warp start kPostR cells apart, which would
+// put 8 lanes of a 16-byte shared load on 2 bank groups; one pad cell after every 4 cells (position
+// c + c / 4) spreads them over all 8 (5 t mod 8 is a permutation).  Accumulation order per sample is
+// chunk -> tap -> channel, as in the scalar version.
 constexpr int kPostThreads = 128, kPostR = 4, kPostTile = kPostThreads * kPostR, kPostGC = 4;
+__host__ __device__ constexpr int post_padded(int c) { return c + (c >> 2); }
+template <int K>
+__host__ __device__ constexpr int post_col_cells() { return post_padded(kPostTile + K - 1) + 1; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 template <int P, int K>
 __global__ void __launch_bounds__(kPostThreads)
 tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                   float* __restrict__ y, int C, int T, int pad, long long bstride, long long pstride,
                   const int* __restrict__ len_rows, const int* __restrict__ valid_len) {
     constexpr int CW = Prec<P>::CW;
-    constexpr int ROWS = kPostTile + K - 1;
+    constexpr int ROWS = kPostTile + K - 1, COL = post_col_cells<K>();
     extern __shared__ __align__(16) uint8_t post_smem[];
     const int n_chunks = C / CW;
-    uint4* cells = reinterpret_cast<uint4*>(post_smem);     // [kPostGC][ROWS]: one group of chunk columns at a time
-    float* wsm = reinterpret_cast<float*>(cells + (size_t)kPostGC * ROWS);    // [chunk][K][CW]
-    for (int e = threadIdx.x; e < C * K; e += blockDim.x) {
-        const int ci = e / K, j = e - ci * K;               // w is [C][K]
-        wsm[((ci / CW) * K + j) * CW + (ci % CW)] = w[e];
-    }
+    uint4* cells = reinterpret_cast<uint4*>(post_smem);     // [kPostGC][COL]: one group of chunk columns at a time
+    float* wsm = reinterpret_cast<float*>(cells + (size_t)kPostGC * COL);     // [chunk][K][CW]
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * kPostTile;
     // variable-length batches: samples at or beyond valid_len[b] are zeros; tiles beyond the rows that were
@@ -755,6 +761,10 @@ tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, c
     if (len_rows && t0 >= len_rows[b]) {
         for (int e = threadIdx.x; e < kPostTile && t0 + e < T; e += blockDim.x) y[(size_t)b * T + t0 + e] = 0.f;
         return;
+    }
+    for (int e = threadIdx.x; e < C * K; e += blockDim.x) {
+        const int ci = e / K, j = e - ci * K;               // w is [C][K]
+        wsm[((ci / CW) * K + j) * CW + (ci % CW)] = w[e];
     }
     // rows t0 - pad .. t0 - pad + ROWS: the planes carry kPadL zero rows in front of the data and the tile
     // overhang behind it (tc_tp); rows past T + kZeroTail may hold anything but only feed samples >= T
@@ -765,12 +775,13 @@ tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, c
     for (int i = 0; i < kPostR; ++i) acc[i] = 0.f;
     for (int c0 = 0; c0 < n_chunks; c0 += kPostGC) {
         const int gc = (n_chunks - c0) < kPostGC ? (n_chunks - c0) : kPostGC;
-        __syncthreads();                                    // previous group consumed (and wsm written)
+        __syncthreads();                                    // previous group consumed
         for (int e = threadIdx.x; e < gc * ROWS; e += blockDim.x) {
             const int chunk = e / ROWS, r = e - chunk * ROWS;
-            cells[e] = *reinterpret_cast<const uint4*>(base + (long long)(c0 + chunk) * pstride + (long long)r * 16);
+            cp_async16(cells + chunk * COL + post_padded(r), base + (long long)(c0 + chunk) * pstride + (long long)r * 16);
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // staged cells (and, first time round, wsm) visible
         for (int chunk = 0; chunk < gc; ++chunk) {
             float wv[K][CW];
 #pragma unroll
@@ -779,11 +790,12 @@ tc_conv_post_tanh(const uint8_t* __restrict__ in, const float* __restrict__ w, c
                 for (int i = 0; i < CW; i += 4)
                     *reinterpret_cast<float4*>(&wv[j][i]) =
                         *reinterpret_cast<const float4*>(wsm + ((c0 + chunk) * K + j) * CW + i);
-            const uint4* col = cells + chunk * ROWS + tl;
+            // cell tl + m sits at post_padded(tl + m) = 5 * tid + m + m / 4   (tl = 4 * tid)
+            const uint4* col = cells + chunk * COL + 5 * threadIdx.x;
 #pragma unroll
             for (int m = 0; m < kPostR + K - 1; ++m) {      // window row m feeds sample r through tap j = m - r
                 float v[CW];
-                cell_to_floats<P>(col[m], v);
+                cell_to_floats<P>(col[m + (m >> 2)], v);
 #pragma unroll
                 for (int r = 0; r < kPostR; ++r) {
                     const int j = m - r;

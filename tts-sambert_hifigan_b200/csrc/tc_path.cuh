@@ -859,7 +859,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
     {
         const int Tw = cur->T;
         dim3 grid((Tw + kPostTile - 1) / kPostTile, B);
-        const size_t post_smem = (size_t)kPostGC * (kPostTile + 6) * 16 + sizeof(float) * h->post_cin * 7;
+        const size_t post_smem = (size_t)kPostGC * post_col_cells<7>() * 16 + sizeof(float) * h->post_cin * 7;
         h->stage_begin(st, "tail");
         h->prof_begin(st, "conv_post", 2.0 * h->post_cin * 7 * (double)B * Tw,
                       (double)B * Tw * (ESZ * h->post_cin + 4.0));
