@@ -118,6 +118,7 @@ def test_cuda_decoder_matches_reference_frames(capsys):
     assert torch.equal(short, mel[:, :10])                 # a prefix is a prefix (causal)
     assert dec.last_launch_count > 10 * 70
     # the reference's progress prints, line for line (models/ar_decoder.py:187-236)
+    capsys.readouterr()
     dec.verbose = True
     with torch.no_grad():
         dec(hvar[:2, :3].contiguous())

@@ -29,25 +29,32 @@
 namespace hfg {
 
 // ------------------------------------------------------------------ kernels
-// Y[m, n] = act(sum_k X[m, k] W[n, k] + bias[n] + add_row[n]) for an M x N tile of 64 x 64 per block.
+// Y[m, n] = act(sum_k X[m, k] W[n, k] + bias[n] + add_row[n]) for an M x N tile of 64 x TN per block
+// (TN = 64: the once-per-call memory projection with thousands of rows; TN = 16: the per-step matrices, whose
+// M = batch <= 64 rows would otherwise leave all but N / 64 SMs idle).  Fixed summation order over k.
 // `step` (device) offsets add_row by *step * add_row_stride (the positional-encoding row of this step).
-template <bool RELU>
+template <bool RELU, int TN>
 __global__ void __launch_bounds__(256)
 ard_gemm(const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
          const float* __restrict__ add_row, long long add_row_stride, const int* __restrict__ step,
          float* __restrict__ Y, int ldy, int M, int N, int K) {
+    constexpr int RG = 256 / TN, RPT = 64 / RG;                       // row groups, rows per thread
     __shared__ float Xs[64][33];
-    __shared__ float Ws[64][33];
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;           // column inside the tile, row group
-    const int n0 = blockIdx.x * 64, m0 = blockIdx.y * 64;
-    float acc[16];
+    __shared__ float Ws[TN][33];
+    const int tx = threadIdx.x % TN, ty = threadIdx.x / TN;           // column inside the tile, row group
+    const int n0 = blockIdx.x * TN, m0 = blockIdx.y * 64;
+    float acc[RPT];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+    for (int r = 0; r < RPT; ++r) acc[r] = 0.f;
     for (int k0 = 0; k0 < K; k0 += 32) {
         for (int e = threadIdx.x; e < 64 * 32; e += 256) {
             const int r = e >> 5, c = e & 31;
-            const int m = m0 + r, n = n0 + r, k = k0 + c;
+            const int m = m0 + r, k = k0 + c;
             Xs[r][c] = (m < M && k < K) ? X[(size_t)m * ldx + k] : 0.f;
+        }
+        for (int e = threadIdx.x; e < TN * 32; e += 256) {
+            const int r = e >> 5, c = e & 31;
+            const int n = n0 + r, k = k0 + c;
             Ws[r][c] = (n < N && k < K) ? W[(size_t)n * K + k] : 0.f;
         }
         __syncthreads();
@@ -55,7 +62,7 @@ ard_gemm(const float* __restrict__ X, int ldx, const float* __restrict__ W, cons
         for (int kk = 0; kk < 32; ++kk) {
             const float w = Ws[tx][kk];
 #pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r] = fmaf(Xs[ty + 4 * r][kk], w, acc[r]);
+            for (int r = 0; r < RPT; ++r) acc[r] = fmaf(Xs[ty + RG * r][kk], w, acc[r]);
         }
         __syncthreads();
     }
@@ -64,8 +71,8 @@ ard_gemm(const float* __restrict__ X, int ldx, const float* __restrict__ W, cons
     float b = bias ? bias[n] : 0.f;
     if (add_row) b += add_row[(step ? (long long)(*step) : 0ll) * add_row_stride + n];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const int m = m0 + ty + 4 * r;
+    for (int r = 0; r < RPT; ++r) {
+        const int m = m0 + ty + RG * r;
         if (m >= M) continue;
         float v = acc[r] + b;
         if (RELU) v = fmaxf(v, 0.f);
@@ -380,9 +387,15 @@ int hfg_ard_decode(hfg_ard_handle* h, const float* hvar, int32_t B, int32_t T, i
     int64_t* counter = &setup;
     auto gemm = [&](bool relu, const float* X, int ldx, const float* Wt, const float* b, const float* add_row, long long add_stride,
                     const int* stp, float* Y, int ldy, int M, int N, int K) {
-        dim3 grid((N + 63) / 64, (M + 63) / 64);
-        if (relu) ard_gemm<true><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
-        else ard_gemm<false><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+        if (M > 256) {                                     // many rows: wide tiles
+            dim3 grid((N + 63) / 64, (M + 63) / 64);
+            if (relu) ard_gemm<true, 64><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+            else ard_gemm<false, 64><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+        } else {                                           // a decode step: narrow tiles so that N / 16 SMs work
+            dim3 grid((N + 15) / 16, (M + 63) / 64);
+            if (relu) ard_gemm<true, 16><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+            else ard_gemm<false, 16><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+        }
         check_cuda(cudaGetLastError(), "ard_gemm launch");
         ++*counter;
     };

@@ -140,6 +140,31 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     } while (!ok);
 }
+// Wait of the EPILOGUE warps: between polls the warp sleeps (doubling up to `max_ns`), so that eight to
+// sixteen waiting warps do not spend the issue slots the working warps of the co-resident CTA need.  A
+// committed ncu source view of the narrow k = 3 pair kernel showed ~40 % of all executed instructions inside
+// these poll loops (profiles/r2_tuning.md).  max_ns = 0: plain spin (mbar_wait).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t max_ns) {
+    uint32_t ok, ns = 32, spins = 0;
+    long long t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (max_ns) {
+            __nanosleep(ns);
+            ns = ns < max_ns ? ns * 2 : max_ns;
+        }
+        if ((++spins & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
+    } while (true);
+}
 // non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;

@@ -58,6 +58,7 @@ struct TcPairArgs {
     int tap_group;    // taps per W stage
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
+    int epi_sleep_ns; // epilogue warps: longest sleep between polls of a barrier (0 = spin)
     int dbg;          // HFG_TUNING builds only -- timing experiments (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
     int tiles_per_batch, n_tiles;
     // variable-length batches: rows of this stage that utterance b needs (valid frames + receptive halo, scaled to
@@ -385,7 +386,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // ---------- pre2: acc2 <- x + b2 (+ partial MRF sum), per K block as it lands ----------
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
-                mbar_wait(A_FULL(sa_i), sa_ph);
+                mbar_wait_sleep(A_FULL(sa_i), sa_ph, (uint32_t)a.epi_sleep_ns);
                 if (kb == 0 && e == 0) HFG_TL(5, it);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
                 for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
@@ -431,7 +432,7 @@ tc_pair_kernel(const TcPairArgs a) {
             }
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
             if (e == 0) HFG_TL(6, it);
-            mbar_wait(ACC1_FULL, it & 1);
+            mbar_wait_sleep(ACC1_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(7, it);
             // only tiles that touch an utterance edge have H rows outside [0, T) to zero
@@ -474,7 +475,7 @@ tc_pair_kernel(const TcPairArgs a) {
             }
             // ---------- epi2: acc2 -> global ----------
             if (e == 0) HFG_TL(8, it);
-            mbar_wait(ACC2_FULL, it & 1);
+            mbar_wait_sleep(ACC2_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(9, it);
             for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {

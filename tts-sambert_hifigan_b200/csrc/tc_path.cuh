@@ -423,6 +423,7 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
     if (n_items > 0x7fffffffLL) return false;                          // item index is an int in the kernel
     ua.n_items = (int)n_items;
     ua.cout_total = cout;
+    ua.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
     const size_t smem = smem_need(MT, sa, sw);
     const int grid = std::min(ua.n_items, h->sm_count);
     if (env_int("HFG_TC_VERBOSE", 0))
@@ -559,6 +560,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.w2_half_stride = L.c2.tc.half_stride[P2][vk];
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
+    a.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
     a.dbg = env_int("HFG_TC_DBG", 0);
     a.b1 = L.c1.bias; a.b2 = L.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;

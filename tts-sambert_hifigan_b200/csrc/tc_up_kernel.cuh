@@ -23,6 +23,7 @@ struct TcUpArgs {
     int pn_per_tile;     // phases * channel tiles: items of one tile are adjacent (they share the activation tile)
     int n_ctile;         // channel tiles per phase
     int cout_total;      // bias entries staged in shared memory (virtual channels when phases are stacked)
+    int epi_sleep_ns;    // epilogue warps: longest sleep between polls of the accumulator barrier (0 = spin)
 };
 
 template <int P>
@@ -212,7 +213,7 @@ tc_up_kernel(const TcUpArgs ua) {
             const int b = tile / a.tiles_per_batch;
             const int q0 = (tile % a.tiles_per_batch) * MT * 128;
             const uint32_t buf = it & 1u;
-            mbar_wait(ACC_FULL(buf), (it >> 1) & 1u);
+            mbar_wait_sleep(ACC_FULL(buf), (it >> 1) & 1u, (uint32_t)ua.epi_sleep_ns);
             tc_fence_after();
             for (int mt = 0; mt < MT; ++mt) {
                 const int q = q0 + mt * 128 + qlane;
