@@ -83,10 +83,10 @@ def test_mirror_keeps_the_reference_schema():
             assert torch.equal(new.state_dict()[k], v), k
 
 
-def _record(case, err, peak, **kw):
+def _record(case, err, peak, mode="fp32", **kw):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "parity_r2.jsonl"), "a") as f:
-        f.write(json.dumps(dict(case=case, mode="fp32", max_abs=err, ref_peak=peak, **kw)) + "\n")
+        f.write(json.dumps(dict(case=case, mode=mode, max_abs=err, ref_peak=peak, **kw)) + "\n")
 
 
 def _cuda_decoder():
@@ -179,7 +179,7 @@ def test_config5_batch64_end_to_end():
         torch.cuda.synchronize()
         e = float(np.abs(wav.cpu().numpy() - ref_wav).max())
         print(f"config5 B=64 wav[{mode}] max-abs vs oracle on the reference mel {e:.3e} (peak {np.abs(ref_wav).max():.3f})")
-        _record("config5_b64_wav_" + mode, e, float(np.abs(ref_wav).max()))
+        _record("config5_b64_wav", e, float(np.abs(ref_wav).max()), mode=mode)
         assert wav.shape == (64, 1, T * 256) and e <= tol
         for i in range(B):                                 # length-aware run: valid region identical
             n = int(lens[i]) * 256

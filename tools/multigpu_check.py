@@ -18,7 +18,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 cfg = synth.DEFAULT_CONFIG
-for mode in ("tf32", "bf16"):
+for mode in ("tf32", "fp16", "bf16"):
     gen = pkg.HiFiGANGenerator(**cfg, mode=mode).to(dev)
     gen.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_weights(cfg, 0).items()})
     mel = torch.from_numpy(synth.make_mel(3, 2 * world + 1, 80, 64)).to(dev)       # ragged utterance split
