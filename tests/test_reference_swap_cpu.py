@@ -115,3 +115,24 @@ def test_wrapper_print_contract_with_swapped_generator(ref_hifigan_cls, monkeypa
     got, wav_new = stdout_of(ref)
     assert got == want
     assert wav_new.shape == wav_ref.shape and wav_new.dtype == wav_ref.dtype == torch.float32
+
+
+def test_decoder_and_length_regulator_swap_under_reference_acoustic_model():
+    """the reference SAMBERTAcousticModel (models/acoustic_model.py:171-178, :258) with its
+    O(T^2) decoder and its length regulator replaced by the B200 mirrors keeps its own state_dict key for key."""
+    sys.path.insert(0, REF)
+    try:
+        from models.acoustic_model import SAMBERTAcousticModel
+    finally:
+        sys.path.remove(REF)
+    model = _build(SAMBERTAcousticModel)
+    before = {k: v.clone() for k, v in model.state_dict().items()}
+    old = model.ar_decoder
+    model.ar_decoder = pkg.PNCAARDecoder.from_reference(old, verbose=False)
+    model.variance_adaptor.length_regulator = pkg.LengthRegulator()
+    after = model.state_dict()
+    assert list(after) == list(before)
+    for k, v in before.items():
+        assert torch.equal(after[k], v), k
+    assert (model.ar_decoder.d_model, model.ar_decoder.n_mels, model.ar_decoder.n_layers, model.ar_decoder.n_heads,
+            model.ar_decoder.chunk_size) == (old.d_model, old.n_mels, old.n_layers, old.n_heads, old.chunk_size)
