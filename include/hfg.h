@@ -161,6 +161,17 @@ int hfg_forward_host(hfg_handle* h, const float* mel_host, int32_t batch, int32_
 int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int32_t frames,
                         float* wav_host, int32_t mode, uint32_t flags);
 
+/* Streaming form of the host-buffer call, for callers that generate batch after batch: up to two submissions
+ * (slot 0 / 1) are in flight.  Submit queues the H2D copy of `mel_host`, the forward (CUDA-graph replay) and the
+ * D2H copy into `wav_host` on three streams of the handle and returns at once; wait(slot) blocks until that
+ * slot's waveform has landed.  The copies of one submission overlap the kernels of its neighbours, so a steady
+ * stream of batches runs at the device rate.  Both host buffers MUST be page-locked and must stay untouched until
+ * wait(slot) returns; a slot must be waited for before it is submitted again (HFG_ERR_STATE otherwise).  Results are
+ * identical to hfg_forward_host. */
+int hfg_forward_host_submit(hfg_handle* h, int32_t slot, const float* mel_host, int32_t batch, int32_t frames,
+                            float* wav_host, int32_t mode);
+int hfg_forward_host_wait(hfg_handle* h, int32_t slot);
+
 /* Per-launch device timing.  When enabled, every kernel launch of hfg_forward*
  * is bracketed by a CUDA event pair on the launching stream; hfg_get_profile
  * synchronises and returns a JSON array, one entry per kernel label:

@@ -193,6 +193,37 @@ def test_host_buffer_path_equals_device_path(mode):
     assert np.array_equal(host.numpy(), dev)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_generate_stream_equals_forward(mode):
+    """hfg_forward_host_submit / _wait (two submissions in flight, copies under the neighbours' kernels): every
+    waveform equals the plain forward bit for bit, in order, across a geometry change in mid-stream; a slot cannot
+    be submitted twice."""
+    cfg = synth.DEFAULT_CONFIG
+    gen = make_gen(cfg, synth.make_weights(cfg, 2), mode)
+    mels = [synth.make_mel(20 + i, 2 + (i % 2), 80, 30 + 7 * (i % 3)) for i in range(7)]
+    want = [run(gen, m) for m in mels]
+    got = list(gen.generate_stream(torch.from_numpy(m).pin_memory() if i % 2 else torch.from_numpy(m)
+                                   for i, m in enumerate(mels)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert not g.is_cuda and g.is_pinned() and np.array_equal(g.numpy(), w)
+    it = gen.generate_stream(torch.from_numpy(m) for m in mels)
+    first = next(it)                                  # early exit: the generator drains what is in flight
+    it.close()
+    assert np.array_equal(first.numpy(), want[0])
+    h = gen._handle_for(torch.device("cuda", 0))
+    m0 = torch.from_numpy(mels[0]).pin_memory()
+    out = torch.empty((m0.shape[0], 1, m0.shape[2] * 256), pin_memory=True)
+    h.forward_host_submit(0, m0.data_ptr(), m0.shape[0], m0.shape[2], out.data_ptr(), _capi.MODES[mode])
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward_host_submit(0, m0.data_ptr(), m0.shape[0], m0.shape[2], out.data_ptr(), _capi.MODES[mode])
+    assert e.value.code == _capi.ERR_STATE
+    h.forward_host_wait(0)
+    assert np.array_equal(out.numpy(), want[0])
+    with pytest.raises(_capi.HfgError):
+        h.forward_host_wait(0)
+
+
 @pytest.mark.parametrize("mode", TC_MODES)
 def test_host_path_graph_replay_and_invalidation(mode):
     """hfg_forward_host captures the launch sequence into a CUDA graph on the second call with the same

@@ -19,7 +19,7 @@ SYMBOLS = [
     "hfg_forward_stages", "hfg_forward_host", "hfg_forward_host_ex", "hfg_last_launch_count",
     "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer", "hfg_set_mel_layout",
     "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
-    "hfg_forward_lengths", "hfg_receptive_radius",
+    "hfg_forward_lengths", "hfg_receptive_radius", "hfg_forward_host_submit", "hfg_forward_host_wait",
 ]
 # include/hfg_mel.h (on-device log-mel / log-mel L1)
 MEL_SYMBOLS = ["hfg_mel_create", "hfg_mel_destroy", "hfg_mel_last_error", "hfg_mel_frames", "hfg_log_mel", "hfg_log_mel_l1"]
@@ -111,6 +111,10 @@ def load():
     lib.hfg_length_regulate_frames.argtypes = [vp, i32, i32, i64p, vp]
     lib.hfg_length_regulate.restype = ctypes.c_int
     lib.hfg_length_regulate.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.hfg_forward_host_submit.restype = ctypes.c_int
+    lib.hfg_forward_host_submit.argtypes = [vp, i32, vp, i32, i32, vp, i32]
+    lib.hfg_forward_host_wait.restype = ctypes.c_int
+    lib.hfg_forward_host_wait.argtypes = [vp, i32]
     lib.hfg_forward_lengths.restype = ctypes.c_int
     lib.hfg_forward_lengths.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, ctypes.c_size_t, i32, vp]
     lib.hfg_receptive_radius.restype = ctypes.c_int
@@ -249,6 +253,12 @@ class Handle:
                      mel_pinned: bool = False, wav_pinned: bool = False):
         flags = (1 if mel_pinned else 0) | (2 if wav_pinned else 0)
         self._check(self._lib.hfg_forward_host_ex(self._h, mel_ptr, batch, frames, wav_ptr, mode, flags))
+
+    def forward_host_submit(self, slot: int, mel_ptr: int, batch: int, frames: int, wav_ptr: int, mode: int):
+        self._check(self._lib.hfg_forward_host_submit(self._h, slot, mel_ptr, batch, frames, wav_ptr, mode))
+
+    def forward_host_wait(self, slot: int):
+        self._check(self._lib.hfg_forward_host_wait(self._h, slot))
 
     def set_mel_layout(self, frames_last: bool):
         self._check(self._lib.hfg_set_mel_layout(self._h, 1 if frames_last else 0))

@@ -423,6 +423,52 @@ static void do_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
 
 using namespace hfg;
 
+// Forward on the handle's own stream and buffers, replayed from a CUDA graph where possible.  First call with a
+// given geometry: plain launches (lazy initialisation happens here).  Second call: the same sequence is captured
+// into a graph.  From then on: one cudaGraphLaunch per forward.
+static void run_graphed(hfg_handle* h, hfg_handle::HostGraph& G, float* dev_mel, float* dev_wav, int batch, int frames, int mode) {
+    static const bool graphs_on = []() { const char* e = getenv("HFG_HOST_GRAPH"); return !e || atoi(e) != 0; }();
+    const bool same = G.B == batch && G.T == frames && G.mode == mode && G.layout == h->mel_layout &&
+                      G.mel == dev_mel && G.wav == dev_wav && G.ws == h->dev_ws;
+    if (!same) {
+        const bool failed = G.failed;
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        G = hfg_handle::HostGraph{};
+        G.failed = failed;
+        G.B = batch; G.T = frames; G.mode = mode; G.layout = h->mel_layout;
+        G.mel = dev_mel; G.wav = dev_wav; G.ws = h->dev_ws;
+    }
+    const bool use_graph = graphs_on && !G.failed && h->profiling == 0;
+    if (use_graph && G.exec) {
+        check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
+        h->launches = G.launches;
+    } else if (use_graph && G.calls >= 1) {
+        cudaGraph_t graph = nullptr;
+        check_cuda(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+        bool ok = true;
+        std::string why;
+        try {
+            do_forward(h, dev_mel, batch, frames, dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+        } catch (const std::exception& e) { ok = false; why = e.what(); }
+        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (ok && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+            G.launches = h->launches;
+            check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
+        } else {
+            // capture not possible here: remember that and run the plain sequence
+            cudaGetLastError();
+            G.exec = nullptr;
+            G.failed = true;
+            do_forward(h, dev_mel, batch, frames, dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+        }
+        if (graph) cudaGraphDestroy(graph);
+    } else {
+        do_forward(h, dev_mel, batch, frames, dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
+    }
+    G.calls++;
+}
+
 #define HFG_TRY(h)  try {
 #define HFG_CATCH(h)                                                         \
     } catch (const StatusError& e) {                                         \
@@ -605,52 +651,55 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
     const float* src = mel_host;
     if (!mel_pinned) { memcpy(h->pin_mel, mel_host, mel_bytes); src = h->pin_mel; }
     check_cuda(cudaMemcpyAsync(h->dev_mel, src, mel_bytes, cudaMemcpyHostToDevice, h->stream), "H2D mel");
-    // First call with a given geometry: plain launches (lazy initialisation happens here).  Second call:
-    // the same sequence is captured into a graph.  From then on: one cudaGraphLaunch per forward.
-    auto& G = h->host_graph;
-    static const bool graphs_on = []() { const char* e = getenv("HFG_HOST_GRAPH"); return !e || atoi(e) != 0; }();
-    const bool same = G.B == batch && G.T == frames && G.mode == mode && G.layout == h->mel_layout &&
-                      G.mel == h->dev_mel && G.wav == h->dev_wav && G.ws == h->dev_ws;
-    if (!same) {
-        const bool failed = G.failed;
-        h->drop_host_graph();
-        G.failed = failed;
-        G.B = batch; G.T = frames; G.mode = mode; G.layout = h->mel_layout;
-        G.mel = h->dev_mel; G.wav = h->dev_wav; G.ws = h->dev_ws;
-    }
-    const bool use_graph = graphs_on && !G.failed && h->profiling == 0;
-    if (use_graph && G.exec) {
-        check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
-        h->launches = G.launches;
-    } else if (use_graph && G.calls >= 1) {
-        cudaGraph_t graph = nullptr;
-        check_cuda(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
-        bool ok = true;
-        std::string why;
-        try {
-            do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
-        } catch (const std::exception& e) { ok = false; why = e.what(); }
-        const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-        if (ok && ce == cudaSuccess && graph &&
-            cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
-            G.launches = h->launches;
-            check_cuda(cudaGraphLaunch(G.exec, h->stream), "cudaGraphLaunch");
-        } else {
-            // capture not possible here: remember that and run the plain sequence
-            cudaGetLastError();
-            G.exec = nullptr;
-            G.failed = true;
-            do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
-        }
-        if (graph) cudaGraphDestroy(graph);
-    } else {
-        do_forward(h, h->dev_mel, batch, frames, h->dev_wav, h->dev_ws, h->dev_ws_bytes, mode, h->stream, nullptr);
-    }
-    G.calls++;
+    run_graphed(h, h->host_graph, h->dev_mel, h->dev_wav, batch, frames, mode);
     float* dst = wav_pinned ? wav_host : h->pin_wav;
     check_cuda(cudaMemcpyAsync(dst, h->dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->stream), "D2H wav");
     check_cuda(cudaStreamSynchronize(h->stream), "stream sync");
     if (!wav_pinned) memcpy(wav_host, h->pin_wav, wav_bytes);
+    HFG_CATCH(h)
+}
+
+int hfg_forward_host_submit(hfg_handle* h, int32_t slot, const float* mel_host, int32_t batch, int32_t frames,
+                            float* wav_host, int32_t mode) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
+    if (slot < 0 || slot >= hfg_handle::kHostSlots || !mel_host || !wav_host || batch <= 0 || frames <= 0)
+        throw StatusError(HFG_ERR_INVALID, "hfg_forward_host_submit: bad argument");
+    auto& S = h->slots[slot];
+    if (S.busy) throw StatusError(HFG_ERR_STATE, "slot still in flight: call hfg_forward_host_wait first");
+    check_cuda(cudaSetDevice(h->device), "cudaSetDevice");
+    int64_t tout = 0;
+    hfg_out_len(h, frames, &tout);
+    const size_t mel_bytes = sizeof(float) * (size_t)batch * h->cfg.n_mels * frames;
+    const size_t wav_bytes = sizeof(float) * (size_t)batch * tout;
+    size_t ws_bytes = 0;
+    if (mode == HFG_MODE_FP32) ws_bytes = workspace_fp32(h, batch, frames);
+    else if (tc_is_tc_mode(mode)) ws_bytes = tc_workspace_bytes(h, batch, frames, mode);
+    else throw StatusError(HFG_ERR_INVALID, "unknown mode");
+    h->ensure_stream_path(slot, mel_bytes, wav_bytes, ws_bytes);
+    // H2D on the copy-in stream, forward on the compute stream once it has landed, D2H on the copy-out stream once
+    // the forward is done: the copies of neighbouring submissions overlap this one's kernels
+    check_cuda(cudaMemcpyAsync(S.dev_mel, mel_host, mel_bytes, cudaMemcpyHostToDevice, h->copy_in), "H2D mel");
+    check_cuda(cudaEventRecord(S.ev_h2d, h->copy_in), "cudaEventRecord(h2d)");
+    check_cuda(cudaStreamWaitEvent(h->stream, S.ev_h2d, 0), "cudaStreamWaitEvent(h2d)");
+    run_graphed(h, S.graph, S.dev_mel, S.dev_wav, batch, frames, mode);
+    check_cuda(cudaEventRecord(S.ev_done, h->stream), "cudaEventRecord(done)");
+    check_cuda(cudaStreamWaitEvent(h->copy_out, S.ev_done, 0), "cudaStreamWaitEvent(done)");
+    check_cuda(cudaMemcpyAsync(wav_host, S.dev_wav, wav_bytes, cudaMemcpyDeviceToHost, h->copy_out), "D2H wav");
+    check_cuda(cudaEventRecord(S.ev_d2h, h->copy_out), "cudaEventRecord(d2h)");
+    S.busy = true;
+    HFG_CATCH(h)
+}
+
+int hfg_forward_host_wait(hfg_handle* h, int32_t slot) {
+    if (!h) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (slot < 0 || slot >= hfg_handle::kHostSlots) throw StatusError(HFG_ERR_INVALID, "hfg_forward_host_wait: bad slot");
+    auto& S = h->slots[slot];
+    if (!S.busy) throw StatusError(HFG_ERR_STATE, "nothing in flight on this slot");
+    S.busy = false;
+    check_cuda(cudaEventSynchronize(S.ev_d2h), "cudaEventSynchronize(d2h)");
     HFG_CATCH(h)
 }
 

@@ -172,9 +172,25 @@ struct hfg_handle {
         cudaGraphExec_t exec = nullptr;
         bool failed = false;
     } host_graph;
+    // streaming host path (hfg_forward_host_submit / _wait): kHostSlots submissions in flight, each with its own
+    // device mel / wav buffers and graph; one workspace and one compute stream, so forwards run back to back
+    // while the neighbours' copies ride on two copy streams
+    static constexpr int kHostSlots = 2;
+    struct HostSlot {
+        float* dev_mel = nullptr; size_t dev_mel_bytes = 0;
+        float* dev_wav = nullptr; size_t dev_wav_bytes = 0;
+        cudaEvent_t ev_h2d = nullptr, ev_done = nullptr, ev_d2h = nullptr;
+        HostGraph graph;
+        bool busy = false;
+    } slots[kHostSlots];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
     void drop_host_graph() {
         if (host_graph.exec) cudaGraphExecDestroy(host_graph.exec);
         host_graph = HostGraph{};
+        for (auto& s : slots) {
+            if (s.graph.exec) cudaGraphExecDestroy(s.graph.exec);
+            s.graph = HostGraph{};
+        }
     }
 
     // hfg_forward_host resources
@@ -228,8 +244,38 @@ struct hfg_handle {
         grow_dev((void**)&dev_wav, dev_wav_bytes, wav_bytes);
         grow_dev(&dev_ws, dev_ws_bytes, ws_bytes);
     }
+    void ensure_stream_path(int slot, size_t mel_bytes, size_t wav_bytes, size_t ws_bytes) {
+        using hfg::check_cuda;
+        if (!stream) check_cuda(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!copy_in) check_cuda(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!copy_out) check_cuda(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking), "cudaStreamCreate");
+        HostSlot& s = slots[slot];
+        for (cudaEvent_t* e : {&s.ev_h2d, &s.ev_done, &s.ev_d2h})
+            if (!*e) check_cuda(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+        auto grow = [&](void** p, size_t& have, size_t want, bool shared) {
+            if (have >= want) return;
+            // a shared buffer (the workspace) may be in use by the other slot's forward: drain the compute stream first
+            if (shared) check_cuda(cudaStreamSynchronize(stream), "stream sync");
+            if (*p) cudaFree(*p);
+            *p = nullptr; have = 0;
+            check_cuda(cudaMalloc(p, want), "cudaMalloc");
+            have = want;
+        };
+        grow((void**)&s.dev_mel, s.dev_mel_bytes, mel_bytes, false);
+        grow((void**)&s.dev_wav, s.dev_wav_bytes, wav_bytes, false);
+        grow(&dev_ws, dev_ws_bytes, ws_bytes, true);
+    }
     void free_host_path() {
         drop_host_graph();
+        for (auto& s : slots) {
+            if (s.dev_mel) cudaFree(s.dev_mel);
+            if (s.dev_wav) cudaFree(s.dev_wav);
+            for (cudaEvent_t e : {s.ev_h2d, s.ev_done, s.ev_d2h}) if (e) cudaEventDestroy(e);
+            s = HostSlot{};
+        }
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
+        copy_in = copy_out = nullptr;
         if (pin_mel) cudaFreeHost(pin_mel);
         if (pin_wav) cudaFreeHost(pin_wav);
         if (dev_mel) cudaFree(dev_mel);

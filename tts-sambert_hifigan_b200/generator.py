@@ -291,6 +291,54 @@ class HiFiGANGenerator(nn.Module):
             self._workspaces[dev.index] = ws
         return ws
 
+    @torch.no_grad()
+    def generate_stream(self, mels):
+        """Batch after batch from host memory at the device rate: `mels` is an iterable of CPU float32 tensors
+        [B, n_mels, Tfrm] (page-locked ones are used in place, others are staged into pinned memory first); yields
+        one page-locked CPU waveform [B, 1, T_wav] per input, in order.  Two submissions are kept in flight
+        (hfg_forward_host_submit / _wait), so the H2D copy of batch i+1 and the D2H copy of batch i-1 run under
+        the kernels of batch i.  Results are identical to forward(mel_cpu)."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("HiFiGANGenerator (B200) needs a CUDA device: there is no CPU fallback")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        h = self._handle_for(dev)
+        h.set_mel_layout(False)
+        mode = _capi.MODES[self.mode]
+        inflight = [None, None]                              # per slot: (pinned mel kept alive, pinned wav)
+        order = []
+
+        def finish(slot):
+            h.forward_host_wait(slot)
+            _, wav = inflight[slot]
+            inflight[slot] = None
+            return wav
+
+        try:
+            for i, mel in enumerate(mels):
+                self._check_input(mel)
+                if mel.is_cuda:
+                    raise RuntimeError("generate_stream takes host tensors (use forward for CUDA tensors)")
+                slot = i & 1
+                if inflight[slot] is not None:
+                    order.pop(0)
+                    yield finish(slot)
+                src = mel.contiguous()
+                if not src.is_pinned():
+                    src = src.pin_memory()
+                B, _, T = src.shape
+                wav = torch.empty((B, 1, self._stage_shapes(B, T)[-1][2]), dtype=torch.float32, pin_memory=True)
+                h.forward_host_submit(slot, src.data_ptr(), B, T, wav.data_ptr(), mode)
+                inflight[slot] = (src, wav)
+                order.append(slot)
+            while order:
+                yield finish(order.pop(0))
+        finally:
+            for slot in (0, 1):                              # a consumer that stops early must not leave copies in flight
+                if inflight[slot] is not None:
+                    h.forward_host_wait(slot)
+                    inflight[slot] = None
+        self.last_launch_count = h.last_launch_count()
+
     def forward(self, mel: torch.Tensor, _stages: Optional[list] = None, _frames_last: bool = False) -> torch.Tensor:
         """Generate waveform from mel-spectrogram (reference models/hifigan.py:224-261).
 
