@@ -21,7 +21,8 @@ def _check_common(d):
     assert d["metric"].split(" (")[0] in baseline["metric"]
 
 
-@pytest.mark.parametrize("name", ["r1_bench_tf32.json", "r1_bench_bf16.json"])
+@pytest.mark.parametrize("name", ["r1_bench_tf32.json", "r1_bench_bf16.json", "r2_bench_tf32.json", "r2_bench_bf16.json",
+                                  "r2_bench_fp16.json"])
 def test_committed_b200_lines_follow_the_contract(name):
     d = json.load(open(os.path.join(ROOT, "profiles", name)))
     _check_common(d)
@@ -49,3 +50,26 @@ def test_reference_arm_line_live():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_round2_line_carries_the_baseline_configs():
+    """The driver-style line of round 2 also measures BASELINE configs 3, 4 and 1 (sub-records), compares with the
+    ORACLE, times the CPU arm on the full batch, and both arms print the same config dictionary."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_tf32.json")))
+    ref = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_reference_arm.json")))
+    assert d["config"] == ref["config"]
+    assert "full batch" in d["cpu_baseline"]["sample"] and "full batch" in ref["cpu_baseline"]["sample"]
+    for m in ("bf16", "fp16"):
+        c3 = d["config3"][m]
+        assert c3["value"] > 0 and c3["e2e"]["value"] > 0 and "max_abs" in c3["parity_vs_oracle"]
+        assert c3["e2e"]["h2d_bytes_per_step"] == 256 * 80 * 172 * 4 and c3["e2e"]["d2h_bytes_per_step"] == 256 * 172 * 256 * 4
+    assert d["config3"]["scaling"] == "strong"
+    for m, r in d["config4"].items():
+        if isinstance(r, dict):
+            assert r["chunks_equal_unchunked"]["bit_equal"] is True and r["parity_vs_oracle"]["max_abs"] < 1e-3 + (m == "bf16")
+    assert {"tf32", "fp16", "bf16"} <= set(d["config1"])
+    q = d["quality"]
+    assert q["tf32"]["max_abs_vs_oracle"] <= 1e-3 and q["fp16"]["max_abs_vs_oracle"] <= 1e-3
+    assert d["roofline"]["frac"] == pytest.approx(d["roofline"]["achieved"] / d["roofline"]["peak"])
+    n8 = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n8.json")))
+    assert n8["n_gpus"] == 8 and n8["config3"]["bf16"]["value"] >= 1e5 and n8["config3"]["bf16"]["e2e"]["value"] >= 1e5

@@ -80,8 +80,67 @@ ard_gemm(const float* __restrict__ X, int ldx, const float* __restrict__ W, cons
     }
 }
 
-// out[m, :] = LayerNorm(x[m, :] + r[m, :]) * gamma + beta   (one warp per row; d <= 1024, eps as nn.LayerNorm)
-__global__ void ard_add_layernorm(const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ gamma,
+// The per-step matrices (M = batch <= 64 rows per block row): a block owns 16 output columns and one 256-wide
+// chunk of K, holds that whole X chunk (64 x 256) and W chunk (16 x 256) in shared memory, and runs the K loop
+// without a barrier.  grid = (N / 16, M / 64, K / 256): with more than one K chunk (linear2, K = d_ff) the blocks
+// write raw partial sums part[z][m][n] that ard_add_layernorm adds up in a fixed order together with the bias.
+constexpr int kStepKC = 256, kStepTN = 16;
+template <bool RELU>
+__global__ void __launch_bounds__(256)
+ard_gemm_step(const float* __restrict__ X, int ldx, const float* __restrict__ W, const float* __restrict__ bias,
+              const float* __restrict__ add_row, long long add_row_stride, const int* __restrict__ step,
+              float* __restrict__ Y, int ldy, long long part_stride, int M, int N, int K) {
+    extern __shared__ float sm[];
+    float (*Xs)[kStepKC + 1] = reinterpret_cast<float (*)[kStepKC + 1]>(sm);                       // [64][257]
+    float (*Ws)[kStepKC + 1] = reinterpret_cast<float (*)[kStepKC + 1]>(sm + 64 * (kStepKC + 1));  // [16][257]
+    const int tx = threadIdx.x % kStepTN, ty = threadIdx.x / kStepTN;      // column, row group (16 groups x 4 rows)
+    const int n0 = blockIdx.x * kStepTN, m0 = blockIdx.y * 64;
+    // this block's K range: one chunk when K is split over grid.z, all of K otherwise
+    const int k_begin = gridDim.z > 1 ? blockIdx.z * kStepKC : 0;
+    const int k_end = gridDim.z > 1 ? (k_begin + kStepKC < K ? k_begin + kStepKC : K) : K;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = k_begin; k0 < k_end; k0 += kStepKC) {
+        const int kc = (k_end - k0) < kStepKC ? (k_end - k0) : kStepKC;
+        if (k0 > k_begin) __syncthreads();                  // previous chunk consumed
+        for (int e = threadIdx.x; e < 64 * kStepKC; e += 256) {
+            const int r = e / kStepKC, c = e - r * kStepKC;
+            Xs[r][c] = (m0 + r < M && c < kc) ? X[(size_t)(m0 + r) * ldx + k0 + c] : 0.f;
+        }
+        for (int e = threadIdx.x; e < kStepTN * kStepKC; e += 256) {
+            const int r = e / kStepKC, c = e - r * kStepKC;
+            Ws[r][c] = (n0 + r < N && c < kc) ? W[(size_t)(n0 + r) * K + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < kStepKC; ++kk) {
+            const float w = Ws[tx][kk];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(Xs[ty + 16 * r][kk], w, acc[r]);
+        }
+    }
+    const int n = n0 + tx;
+    if (n >= N) return;
+    const bool partial = gridDim.z > 1;
+    float b = 0.f;
+    if (!partial) {
+        b = bias ? bias[n] : 0.f;
+        if (add_row) b += add_row[(step ? (long long)(*step) : 0ll) * add_row_stride + n];
+    }
+    float* Yp = Y + (partial ? (long long)blockIdx.z * part_stride : 0ll);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + ty + 16 * r;
+        if (m >= M) continue;
+        float v = acc[r] + b;
+        if (RELU && !partial) v = fmaxf(v, 0.f);
+        Yp[(size_t)m * ldy + n] = v;
+    }
+}
+
+// out[m, :] = LayerNorm(x[m, :] + r[m, :]) * gamma + beta   (one warp per row; d <= 1024, eps as nn.LayerNorm).
+// r may be split into n_part raw partial sums (split-K GEMM) whose bias `rbias` is added here, in a fixed order.
+__global__ void ard_add_layernorm(const float* __restrict__ x, const float* __restrict__ r, int n_part, long long part_stride,
+                                  const float* __restrict__ rbias, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, float* __restrict__ out, int M, int d, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -90,7 +149,12 @@ __global__ void ard_add_layernorm(const float* __restrict__ x, const float* __re
     float s = 0.f;
     for (int i = 0; i < per; ++i) {
         const int c = lane + 32 * i;
-        v[i] = c < d ? x[(size_t)row * d + c] + r[(size_t)row * d + c] : 0.f;
+        float rv = 0.f;
+        if (c < d) {
+            rv = rbias ? rbias[c] : 0.f;
+            for (int z = 0; z < n_part; ++z) rv += r[(long long)z * part_stride + (size_t)row * d + c];
+        }
+        v[i] = c < d ? x[(size_t)row * d + c] + rv : 0.f;
         s += v[i];
     }
 #pragma unroll
@@ -243,7 +307,7 @@ ArdPlan ard_plan(const hfg_ard_config& c, int B, int T, int max_len) {
     size_t cur = 0;
     auto take = [&](size_t floats) { const size_t off = cur; cur += (floats * 4 + 255) / 256 * 256; return off; };
     p.x = take((size_t)B * c.d_model);
-    p.y = take((size_t)B * c.d_model);
+    p.y = take((size_t)B * c.d_model * std::max(1, (c.d_ff + 255) / 256));       // also the split-K partial sums of linear2
     p.qkv = take((size_t)B * 3 * c.d_model);
     p.att = take((size_t)B * c.d_model);
     p.hid = take((size_t)B * std::max(c.d_ff, c.d_model));
@@ -386,15 +450,17 @@ int hfg_ard_decode(hfg_ard_handle* h, const float* hvar, int32_t B, int32_t T, i
     int64_t per_step = 0, setup = 0;
     int64_t* counter = &setup;
     auto gemm = [&](bool relu, const float* X, int ldx, const float* Wt, const float* b, const float* add_row, long long add_stride,
-                    const int* stp, float* Y, int ldy, int M, int N, int K) {
+                    const int* stp, float* Y, int ldy, int M, int N, int K, bool split_k = false) {
         if (M > 256) {                                     // many rows: wide tiles
             dim3 grid((N + 63) / 64, (M + 63) / 64);
             if (relu) ard_gemm<true, 64><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
             else ard_gemm<false, 64><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
-        } else {                                           // a decode step: narrow tiles so that N / 16 SMs work
-            dim3 grid((N + 15) / 16, (M + 63) / 64);
-            if (relu) ard_gemm<true, 16><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
-            else ard_gemm<false, 16><<<grid, 256, 0, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, M, N, K);
+        } else {                                           // a decode step: 16 columns x one 256-wide K chunk per block
+            dim3 grid((N + kStepTN - 1) / kStepTN, (M + 63) / 64, split_k ? (K + kStepKC - 1) / kStepKC : 1);
+            const size_t smem = (size_t)(64 + kStepTN) * (kStepKC + 1) * sizeof(float);
+            const long long part_stride = (long long)M * ldy;
+            if (relu) ard_gemm_step<true><<<grid, 256, smem, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, part_stride, M, N, K);
+            else ard_gemm_step<false><<<grid, 256, smem, st>>>(X, ldx, Wt, b, add_row, add_stride, stp, Y, ldy, part_stride, M, N, K);
         }
         check_cuda(cudaGetLastError(), "ard_gemm launch");
         ++*counter;
@@ -403,6 +469,8 @@ int hfg_ard_decode(hfg_ard_handle* h, const float* hvar, int32_t B, int32_t T, i
     if (std::max(attn_smem_self, attn_smem_cross) > 200 * 1024)
         throw StatusError(HFG_ERR_UNSUPPORTED, "sequence too long for the attention kernel's score buffer");
     check_cuda(cudaFuncSetAttribute(ard_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(ard_gemm_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "attr");
+    check_cuda(cudaFuncSetAttribute(ard_gemm_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "attr");
 
     // ---- once per call: start token, step counter, encoder memory projected per layer ([B*T, 2d]: K | V) ----
     check_cuda(cudaMemsetAsync(frame, 0, (size_t)B * c.n_mels * sizeof(float), st), "memset(frame)");
@@ -427,8 +495,9 @@ int hfg_ard_decode(hfg_ard_handle* h, const float* hvar, int32_t B, int32_t T, i
             float* Kc = F(p.kcache) + (size_t)i * p.cache_layer;
             float* Vc = F(p.vcache) + (size_t)i * p.cache_layer;
             float* mem = F(p.mem) + (size_t)i * p.mem_layer;
-            auto add_ln = [&](const char* nrm) {
-                ard_add_layernorm<<<(B + 3) / 4, 128, 0, st>>>(x, y, W(L + nrm + "weight"), W(L + nrm + "bias"), x, B, d, 1e-5f);
+            auto add_ln = [&](const char* nrm, int n_part = 1, const float* rbias = nullptr) {
+                ard_add_layernorm<<<(B + 3) / 4, 128, 0, st>>>(x, y, n_part, (long long)B * d, rbias, W(L + nrm + "weight"),
+                                                               W(L + nrm + "bias"), x, B, d, 1e-5f);
                 check_cuda(cudaGetLastError(), "ard_add_layernorm launch");
                 ++*counter;
             };
@@ -450,8 +519,10 @@ int hfg_ard_decode(hfg_ard_handle* h, const float* hvar, int32_t B, int32_t T, i
             add_ln("norm2.");
             // feed-forward
             gemm(true, x, d, W(L + "linear1.weight"), W(L + "linear1.bias"), nullptr, 0, nullptr, hid, c.d_ff, B, c.d_ff, d);
-            gemm(false, hid, c.d_ff, W(L + "linear2.weight"), W(L + "linear2.bias"), nullptr, 0, nullptr, y, d, B, d, c.d_ff);
-            add_ln("norm3.");
+            const int ff_parts = B <= 256 ? (c.d_ff + kStepKC - 1) / kStepKC : 1;   // split-K partial sums land in y[z]
+            gemm(false, hid, c.d_ff, W(L + "linear2.weight"), W(L + "linear2.bias"), nullptr, 0, nullptr, y, d, B, d, c.d_ff,
+                 /*split_k=*/ff_parts > 1);
+            add_ln("norm3.", ff_parts, ff_parts > 1 ? W(L + "linear2.bias") : nullptr);
         }
         gemm(false, x, d, W("mel_proj.weight"), W("mel_proj.bias"), nullptr, 0, nullptr, frame, c.n_mels, B, c.n_mels, d);
         ard_store_frame<<<std::min(64, (B * c.n_mels + 255) / 256), 256, 0, st>>>(frame, mel, B, c.n_mels, max_len, step);
