@@ -261,22 +261,29 @@ def test_kernel_variants_are_bit_identical(mode):
     tuning = os.path.join(root, "tts-sambert_hifigan_b200", "lib", "libhfg_b200_tuning.so")
     assert os.path.exists(tuning), "build() makes the tuning library next to the production one"
     T = {"HFG_LIB_PATH": tuning}
-    variants = [{"HFG_TC_UP_PERSIST": "0", "HFG_TC_PAIR_CTAS": "1", "HFG_TC_DBG": "16"},       # production: knobs are dead
-                dict(T), dict(T, HFG_TC_UP_PERSIST="0"), dict(T, HFG_TC_UP_PERSIST="0", HFG_TC_UPS_STACK="0"),
-                dict(T, HFG_TC_UPS_STACK="1"), dict(T, HFG_TC_UP_RESBLOCK="1", HFG_TC_UP_WIDE="1"),
-                dict(T, HFG_TC_STREAMS="1"), dict(T, HFG_TC_PAIR_CTAS="1"),
-                dict(T, HFG_TC_PAIR_MT="1"), dict(T, HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"),
-                dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0")]
-    hashes = []
-    for v in variants:
-        env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, **v)
-        out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
-                             env=env, capture_output=True, text=True, timeout=300)
-        assert out.returncode == 0, out.stderr[-2000:]
-        line = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
-        hashes.append(line.split()[1])
-        print(v, line)
-    assert len(set(hashes)) == 1, list(zip(variants, hashes))
+    # group A: the default arithmetic (conv2 of the narrow pairs in space-to-depth form); group B: the same network
+    # with that form switched off, which is what tiles of a single 128-row sub-tile (MT = 1) use anyway.  The two
+    # groups sum conv2's taps in a different order, so bit identity holds inside each group.
+    group_a = [{"HFG_TC_UP_PERSIST": "0", "HFG_TC_PAIR_CTAS": "1", "HFG_TC_DBG": "16", "HFG_TC_S2D": "0"},   # production: knobs are dead
+               dict(T), dict(T, HFG_TC_UP_PERSIST="0"), dict(T, HFG_TC_UP_PERSIST="0", HFG_TC_UPS_STACK="0"),
+               dict(T, HFG_TC_UPS_STACK="1"), dict(T, HFG_TC_UP_RESBLOCK="1", HFG_TC_UP_WIDE="1"),
+               dict(T, HFG_TC_STREAMS="1"), dict(T, HFG_TC_PAIR_CTAS="1"),
+               dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0")]
+    group_b = [dict(T, HFG_TC_S2D="0"), dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1"),
+               dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_PAIR_MT="1")]
+    # group C: the space-to-depth form forced onto every layer that can take it (C = 64 too, all k)
+    group_c = [dict(T, HFG_TC_S2D="2"), dict(T, HFG_TC_S2D="2", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_S2D="2", HFG_TC_STREAMS="1")]
+    for variants in (group_a, group_b, group_c):
+        hashes = []
+        for v in variants:
+            env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, **v)
+            out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
+                                 env=env, capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            line = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
+            hashes.append(line.split()[1])
+            print(v, line)
+        assert len(set(hashes)) == 1, list(zip(variants, hashes))
 
 
 def test_debug_prints_match_reference(manifest, capsys):

@@ -41,6 +41,10 @@ struct TcPack {
     // fused-pair kernel packs: [precision][N-halves for a cta_group::2 pair ? 1 : 0][K block of 4 cells ? 1 : 0]
     void* w_pair[3][2][2] = {};
     long long half_stride[3][2] = {};     // [precision][kbc4]: bytes between the two N-halves
+    // conv2 of a narrow fused pair in space-to-depth form (tc_pair_kernel.cuh): (k + 1) / 2 taps of a 2N x 2N matrix,
+    // [precision][N-halves ? 1 : 0]; null where not packed
+    void* w_s2d[3][2] = {};
+    long long s2d_half_stride[3] = {};
     bool ok = false;          // layer shape is covered by the tensor-core path
 };
 

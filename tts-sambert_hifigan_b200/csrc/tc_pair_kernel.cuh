@@ -55,7 +55,14 @@ struct TcPairArgs {
     int RH;           // rows per H plane  >= MT*128 + 2*p2
     int TO;           // output rows per tile = MT*128 - 2*p2
     int sa, sw;
-    int tap_group;    // taps per W stage
+    int tap_group;    // taps per W stage (conv1)
+    // conv2 in space-to-depth form (s2d = 1, narrow layers): GEMM row m of conv2 holds the two time steps 2m, 2m+1
+    // of the tile -- H' has 2N channels (parity, channel), D2 has 2N columns (parity, channel) and MT / 2 sub-tiles,
+    // the k taps collapse into k2 = (k + 1) / 2 taps of a 2N x 2N matrix of which k / (k + 1) is non-zero.  One
+    // A-operand read (the 64 B/clk shared-memory read that bounds the narrow layers) then feeds twice the output
+    // columns: conv2 needs (k + 1) / 2 * 2 MMAs per 256 time steps instead of 2 * k.  s2d = 0: k2 = k, tap_group2 = tap_group.
+    int s2d, k2, tap_group2;
+    unsigned w_stage_bytes;   // bytes of one W ring slot (the larger of the conv1 / conv2 stage)
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
     int epi_sleep_ns; // epilogue warps: longest sleep between polls of a barrier (0 = spin)
@@ -116,11 +123,13 @@ tc_pair_kernel(const TcPairArgs a) {
     const int KBC = a.kbc;                            // 16-byte cells per K block (8, or 4 when smem is tight)
     const int nck_max = n_chunks < KBC ? n_chunks : KBC;
     const int n_kb = (n_chunks + KBC - 1) / KBC;
-    const int n_chunks2 = N / CW2;                    // cells per row of the H tile (conv2's K extent)
+    const int PP = a.s2d ? 2 : 1;                     // time steps per GEMM row of conv2
+    const int N2 = N * PP, NB2 = N2 / CTAS, MT2 = MT / PP, k2 = a.k2;
+    const int n_chunks2 = (N / CW2) * PP;             // cells per row of the H tile (conv2's K extent)
     const int n_kb2 = (n_chunks2 + KBC - 1) / KBC;
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
-    const int G = a.tap_group;
-    const uint32_t w_stage_bytes = (uint32_t)G * NB * nck_max * 16;
+    const int G = a.tap_group, G2 = a.tap_group2;
+    const uint32_t w_stage_bytes = a.w_stage_bytes;
     uint8_t* sA = smem;
     uint8_t* sW = sA + (size_t)a.sa * a_stage_bytes;
     uint8_t* sH = sW + (size_t)a.sw * w_stage_bytes;
@@ -206,7 +215,7 @@ tc_pair_kernel(const TcPairArgs a) {
         // one polling thread: whichever ring has a free slot gets its next copy.  (Issuing them in one
         // blocking program order let a full A ring stall the weight stream and starve the MMAs:
         // profiles/r1_tuning.md section 6.)
-        const int groups = (k + G - 1) / G;
+        const int groups = (k + G - 1) / G, groups2 = (k2 + G2 - 1) / G2;
         int a_sc = next_live(sched0), a_kb = 0;                  // next A block: schedule slot, K block
         int w_sc = a_sc, w_conv = 0, w_kb = 0, w_g = 0;          // next W stage
         int a_t = 0, w_t = 0;                                    // ordinals of those slots among this CTA's live ones
@@ -233,22 +242,24 @@ tc_pair_kernel(const TcPairArgs a) {
             }
             if (w_sc < n_sched && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
                 const int w_chunks = w_conv ? n_chunks2 : n_chunks, w_nkb = w_conv ? n_kb2 : n_kb;
+                const int w_k = w_conv ? k2 : k, w_G = w_conv ? G2 : G, w_groups = w_conv ? groups2 : groups;
+                const int w_NB = w_conv ? NB2 : NB;
                 const int nck = (w_chunks - KBC * w_kb) < KBC ? (w_chunks - KBC * w_kb) : KBC;
-                const int tap0 = w_g * G;
-                const int g = (k - tap0) < G ? (k - tap0) : G;
+                const int tap0 = w_g * w_G;
+                const int g = (w_k - tap0) < w_G ? (w_k - tap0) : w_G;
                 if (w_conv == 0 && w_kb == 0 && w_g == 0) HFG_TL(11, w_t);
                 if (leader && HFG_DBG(a, 1)) mbar_arrive(W_FULL(sw_i));
                 if (leader && !HFG_DBG(a, 1)) {
                     const uint8_t* w = w_conv ? a.w2 : a.w1;
-                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * NB * 16);
+                    mbar_expect_tx(W_FULL(sw_i), (uint32_t)g * nck * w_NB * 16);
                     bulk_g2s(smem_u32(sW + (size_t)sw_i * w_stage_bytes),
                              w + (long long)rank * (w_conv ? a.w2_half_stride : a.w_half_stride) +
-                                 ((long long)w_kb * k * KBC + (long long)tap0 * nck) * NB * 16,
-                             (uint32_t)g * nck * NB * 16, W_FULL(sw_i));
+                                 ((long long)w_kb * w_k * KBC + (long long)tap0 * nck) * w_NB * 16,
+                             (uint32_t)g * nck * w_NB * 16, W_FULL(sw_i));
                 }
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                if (++w_g == groups) { w_g = 0; if (++w_kb == w_nkb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
+                if (++w_g == w_groups) { w_g = 0; if (++w_kb == w_nkb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
                 did = true;
             }
             if (did) { idle = 0; t_idle0 = 0; continue; }
@@ -262,16 +273,17 @@ tc_pair_kernel(const TcPairArgs a) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const bool leader = elect_one();
-        const uint32_t idesc = umma_idesc<P>(N, 128 * CTAS), idesc2 = umma_idesc<P2>(N, 128 * CTAS);
+        const uint32_t idesc = umma_idesc<P>(N, 128 * CTAS), idesc2 = umma_idesc<P2>(N2, 128 * CTAS);
         const uint32_t d_hi = (128u >> 4) | (1u << 14);                     // SBO = 128 B, version 1
         const uint32_t a_lbo = ((uint32_t)R1) << 16, h_lbo = ((uint32_t)RH) << 16, b_lbo = ((uint32_t)NB) << 16;
+        const uint32_t b2_lbo = ((uint32_t)NB2) << 16;
         auto commit = [&](uint32_t bar) { if constexpr (CTAS == 2) tc_commit2(bar); else tc_commit(bar); };
         if (CTAS == 2 && rank == 1) {
             // ---- peer CTA: no MMA issue.  Forward "my stage has landed" to the leader: one lane per ring
             // slot, so slots are forwarded independently instead of through one serial wait chain ----
             int n_my = 0;
             for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step)) ++n_my;
-            const int stages_per_tile = (n_kb + n_kb2) * ((k + G - 1) / G);
+            const int stages_per_tile = n_kb * ((k + G - 1) / G) + n_kb2 * ((k2 + G2 - 1) / G2);
             const int total_w = n_my * stages_per_tile, total_a = n_my * n_kb;
             if (lane < a.sw) {
                 const int uses = total_w / a.sw + (lane < total_w % a.sw ? 1 : 0);
@@ -337,18 +349,18 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int nck = (n_chunks2 - KBC * kb) < KBC ? (n_chunks2 - KBC * kb) : KBC;
                 const int ksteps = nck >> 1;
                 const uint32_t h_lo0 = h_lo_base + (uint32_t)(KBC * kb * RH);
-                for (int tap0 = 0; tap0 < k; tap0 += G) {
-                    const int g = (k - tap0) < G ? (k - tap0) : G;
+                for (int tap0 = 0; tap0 < k2; tap0 += G2) {
+                    const int g = (k2 - tap0) < G2 ? (k2 - tap0) : G2;
                     mbar_wait(W_FULL(sw_i), sw_ph);
                     tc_fence_after();
-                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b2_lbo;
                     if (leader) {
                         for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
-                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
+                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB2);
                             const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : 1));
-                            for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<P2, CTAS>(acc2 + (uint32_t)(mt * N), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB, idesc2, ksteps, 1u);
+                            for (int mt = 0; mt < MT2; ++mt)
+                                umma_ksteps<P2, CTAS>(acc2 + (uint32_t)(mt * N2), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB2, idesc2, ksteps, 1u);
                         }
                         commit(W_EMPTY(sw_i));
                     }
@@ -366,9 +378,14 @@ tc_pair_kernel(const TcPairArgs a) {
         const int e = warp - 2;
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
         const int half = e >> 2;                      // the two warps of a quarter split the sub-tiles ...
-        const bool split_cols = MT == 1;              // ... or, with a single sub-tile, alternate column steps
-        const int mt_first = split_cols ? 0 : half, mt_step = split_cols ? 1 : 2;
-        const int cs = split_cols ? 2 : 1, ch = split_cols ? half : 0;   // 32-column-step stride / phase
+        // ... or, with a single sub-tile, alternate 32-column steps.  acc1 has MT sub-tiles of N columns, acc2 has
+        // MT2 sub-tiles of N2 columns (MT / 2 and 2 N in space-to-depth form): each accumulator has its own split,
+        // and every phase that touches acc2 (pre2, epi2) uses the same one
+        const bool split1 = MT == 1, split2 = MT2 == 1;
+        const int mt_first = split1 ? 0 : half, mt_step = split1 ? 1 : 2;
+        const int cs = split1 ? 2 : 1, ch = split1 ? half : 0;           // acc1: 32-column-step stride / phase
+        const int mt2_first = split2 ? 0 : half, mt2_step = split2 ? 1 : 2;
+        const int cs2 = split2 ? 2 : 1, ch2 = split2 ? half : 0;         // acc2
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
@@ -389,21 +406,22 @@ tc_pair_kernel(const TcPairArgs a) {
                 mbar_wait_sleep(A_FULL(sa_i), sa_ph, (uint32_t)a.epi_sleep_ns);
                 if (kb == 0 && e == 0) HFG_TL(5, it);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
-                for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
-                    const int lr = mt * 128 + row;                      // output row inside the tile
+                for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8); mt += mt2_step) {
+                  for (int pp = 0; pp < PP; ++pp) {                     // the time steps of this GEMM row
+                    const int lr = (mt * 128 + row) * PP + pp;          // output row inside the tile
                     const int t = t0 + lr;
                     const bool add_prev = add_prev_mode && real && lr < a.TO && t < a.T;
                     const uint8_t* rp = sa_p + (size_t)(lr + a.p2 + a.p1) * 16;
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
-                    const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N + kb * KBC * CW);
+                    const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2 + pp * N + kb * KBC * CW);
                     const uint8_t* sump = a.n_sum ? a.sum_in[0] + (long long)b * a.o_bstride + (long long)(kPadL + t) * 16 : nullptr;
                     for (int c16 = 0; c16 < nck * CW; c16 += 16) {              // 16 columns at a time
-                        const int col = kb * KBC * CW + c16;
-                        // column ownership must match epi1 / epi2 (32-column groups alternate between the two
+                        const int col = kb * KBC * CW + c16;                    // channel; acc2 column = pp * N + col
+                        // column ownership must match epi2 (32-column groups of acc2 alternate between the two
                         // warps of a lane quarter): this warp's tcgen05.st for tile i+1 may only touch columns
                         // whose tile-i values it has itself already read in epi2
-                        if (split_cols && ((col >> 5) & 1) != half) continue;
+                        if (split2 && (((pp * N + col) >> 5) & 1) != half) continue;
                         float v[16];
                         load_cells16<P>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
                         float prev[16];
@@ -424,6 +442,7 @@ tc_pair_kernel(const TcPairArgs a) {
                         }
                         tmem_st16(tbase + (uint32_t)c16, v);
                     }
+                  }
                 }
                 tmem_st_wait();
                 __syncwarp();
@@ -441,7 +460,9 @@ tc_pair_kernel(const TcPairArgs a) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
                 const bool drop = edge_tile && !(th >= 0 && th < a.T);  // conv2 zero-pads ITS input
-                uint8_t* hp = sH + (size_t)hr * 16;
+                // H row hr of the tile: row hr of plane chunk, or -- space-to-depth -- row hr / 2 of plane
+                // (hr % 2) * (N / CW2) + chunk
+                uint8_t* hp = a.s2d ? sH + (size_t)(hr >> 1) * 16 + (size_t)(hr & 1) * (N / CW2) * h_plane : sH + (size_t)hr * 16;
                 const uint32_t tbase = acc1 + lane_sel + (uint32_t)(mt * N);
                 for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
                     uint32_t r0[16], r1[16];
@@ -478,17 +499,18 @@ tc_pair_kernel(const TcPairArgs a) {
             mbar_wait_sleep(ACC2_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(9, it);
-            for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
-                const int lr = mt * 128 + row;
-                const int t = t0 + lr;
-                const bool valid = real && lr < a.TO && t < a.T;
-                const long long row_bytes = (long long)(kPadL + t) * 16;
-                const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N);
-                uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
-                uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
-                for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
+            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8); mt += mt2_step) {
+                const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
+                for (int c0 = 32 * ch2; c0 < N2; c0 += 32 * cs2) {
+                    const int pp = c0 >= N ? 1 : 0, cb = c0 - pp * N;   // time step of this GEMM row, channel base (N % 32 == 0 when PP = 2)
+                    const int lr = (mt * 128 + row) * PP + pp;
+                    const int t = t0 + lr;
+                    const bool valid = real && lr < a.TO && t < a.T;
+                    const long long row_bytes = (long long)(kPadL + t) * 16;
+                    uint8_t* ap = reinterpret_cast<uint8_t*>(a.acc) + (long long)b * a.acc_bstride + row_bytes;
+                    uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
                     uint32_t r0[16], r1[16];
-                    const bool two = c0 + 16 < N;
+                    const bool two = cb + 16 < N;
                     tmem_ld16(tbase + (uint32_t)c0, r0);
                     if (two) tmem_ld16(tbase + (uint32_t)(c0 + 16), r1);
                     tmem_ld_wait();
@@ -496,7 +518,7 @@ tc_pair_kernel(const TcPairArgs a) {
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         if (hh == 1 && !two) break;
-                        const int cc = c0 + 16 * hh;
+                        const int cc = cb + 16 * hh;
                         float v[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(hh ? r1[i] : r0[i]);

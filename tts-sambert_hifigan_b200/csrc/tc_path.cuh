@@ -148,6 +148,24 @@ inline void tc_pack_conv(hfg_handle* h, ConvLayer& L, const HostTensor& w, const
     const bool can_halve = L.cout % 32 == 0;
     for (int prec = 0; prec < 3; ++prec) L.tc.w_pair[prec][0][0] = L.tc.w[prec];
     if (can_halve) tc_pack_generic(h, L.tc, L.cin, L.cout, 1, L.k, get, true, true, 8);
+    // Space-to-depth form of a dilation-1 convolution for the narrow layers (conv2 of every pair): GEMM row m holds
+    // time steps 2m and 2m+1, so input "channel" (p'', ci) and output "channel" (p, co) run over 2N values and the k
+    // taps collapse into (k + 1) / 2 taps q with  W'[(p, co), (p'', ci), q] = W[co, ci, 2q + p'' - p]  (0 outside).
+    if (L.dil == 1 && L.cout <= 64 && L.cout % 32 == 0 && L.k % 2 == 1) {
+        const int N = L.cout, k2 = (k + 1) / 2;
+        auto get2 = [&](int n, int ci, int, int q) {
+            const int p = n / N, co = n % N, pi = ci / N, c = ci % N;
+            const int j = 2 * q + pi - p;
+            return (j >= 0 && j < k) ? w.data[((size_t)co * cin + c) * k + j] : 0.f;
+        };
+        for (int prec : {PREC_BF16, PREC_FP16})
+            for (int halves = 0; halves < 2; ++halves) {
+                TcPack tmp;
+                tc_pack_generic(h, tmp, 2 * N, 2 * N, 1, k2, get2, true, halves == 1, 8, prec);
+                L.tc.w_s2d[prec][halves] = tmp.w_pair[prec][halves][0];
+                if (halves) L.tc.s2d_half_stride[prec] = tmp.half_stride[prec][0];
+            }
+    }
     // K blocks of 4 cells let tf32 C=128 run MT=2 tiles, but measured slower than MT=1 with K blocks of 8
     // (profiles/r1_tuning.md): packed only on request (HFG_TC_PACK_KBC4=1, tuning experiments)
     if (L.cin / 4 >= 16 && env_int("HFG_TC_PACK_KBC4", 0)) {
@@ -215,7 +233,7 @@ static inline int tc_prec_of_mode(int mode) {
 }
 static inline bool tc_is_tc_mode(int mode) { return mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16 || mode == HFG_MODE_FP16; }
 
-struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; };
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; int s2d, k2, G2; size_t stage; };
 static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, int prec);
 
 // How the MRF sum (reference models/hifigan.py:126-131) of stage i is formed.
@@ -486,10 +504,22 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
         // A ring: `sa_tiles` tiles of activations in flight (the next tile's rows stream in while this
         // tile is in its conv2 / epilogues)
         const int R1 = MT * 128 + 2 * p1;
-        const int RH = (MT * 128 + 2 * p2 + 7) / 8 * 8;
+        // conv2 in space-to-depth form (narrow layers, 2-byte intermediate): H' has MT * 64 + k2 - 1 rows of 2N channels
+        // Measured per layer (profiles/r2_tuning.md section 9, bf16, us without -> with): C = 32 k = 3 43.2 -> 43.5,
+        // k = 7 57.5 -> 52.5, k = 11 74.3 -> 64.3; C = 64 (CTA pair, N2 = 128) 43 -> 51 / 51 -> 60 / 62 -> 69; tf32 mode
+        // (MT = 2 tiles) 0.714 -> 0.723 ms for stage 3.  Hence: 2-byte modes, C = 32, k >= 5 (HFG_TC_S2D = 2 forces it
+        // wherever it is possible).
+        const int s2d_want = env_int("HFG_TC_S2D", 1);
+        const bool s2d_pays = prec != PREC_TF32 && N <= 32 && k >= 5;
+        const bool s2d = (s2d_want == 2 || (s2d_want == 1 && s2d_pays)) && N <= 64 && N % 32 == 0 && prec2 != PREC_TF32 &&
+                         MT % 2 == 0 && P.c2.tc.w_s2d[prec2][ctas - 1] != nullptr;
+        const int k2 = s2d ? (k + 1) / 2 : k;
+        const int RH = s2d ? (MT * 64 + k2 - 1 + 7) / 8 * 8 : (MT * 128 + 2 * p2 + 7) / 8 * 8;
+        const int h_chunks = s2d ? 2 * n_chunks2 : n_chunks2;
         const size_t tap_bytes = (size_t)NB * nck_max * 16;
+        const size_t tap2_bytes = s2d ? (size_t)(2 * N / ctas) * std::min(kbc, h_chunks) * 16 : tap_bytes;
         const size_t a_stage = (size_t)R1 * nck_max * 16;
-        const size_t fixed0 = (size_t)n_chunks2 * RH * 16 + (size_t)2 * N * 4 + (size_t)env_int("HFG_TC_PAIR_PAD", 512);
+        const size_t fixed0 = (size_t)h_chunks * RH * 16 + (size_t)2 * N * 4 + (size_t)env_int("HFG_TC_PAIR_PAD", 512);
         int ncols = 32;
         while (ncols < 2 * MT * N) ncols <<= 1;
         const int sw_min = std::max(2, env_int("HFG_TC_PAIR_SWMIN", 2));
@@ -510,13 +540,17 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
             };
             while (sa > sa_floor && taps_per_stage(sa) < std::min(k, 3)) --sa;
             const size_t fixed = fixed0 + sa * a_stage;
-            if (fixed + sw_min * tap_bytes > budget) return c;
+            if (fixed + sw_min * std::max(tap_bytes, tap2_bytes) > budget) return c;
             int G = (int)std::min<size_t>((size_t)k, (budget - fixed) / (sw_min * tap_bytes));
             G = (int)std::min<size_t>((size_t)G, std::max<size_t>(1, stage_cap / tap_bytes));
-            const size_t stage = (size_t)G * tap_bytes;
+            // one ring serves both convolutions: a slot holds G taps of conv1 or G2 taps of conv2
+            const size_t stage = std::max((size_t)G * tap_bytes, tap2_bytes);
+            const int G2 = s2d ? (int)std::min<size_t>((size_t)k2, stage / tap2_bytes) : G;
             const int sw = (int)std::min<size_t>(kMaxSW, (budget - fixed) / stage);
+            if (sw < 2) return c;
             c.ctas = ctas; c.kbc = kbc;
             c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2;
+            c.s2d = s2d ? 1 : 0; c.k2 = k2; c.G2 = G2; c.stage = stage;
             c.smem = fixed + (size_t)sw * stage;
             c.occ = std::max(1, std::min((int)((227 * 1024) / (c.smem + 1024)), 512 / ncols));
             c.ok = true;
@@ -555,9 +589,10 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     const int vk = g.kbc == 4 ? 1 : 0;
     const int P2 = tc_pair_p2(P);
     a.w1 = reinterpret_cast<const uint8_t*>(L.c1.tc.w_pair[P][g.ctas - 1][vk]);
-    a.w2 = reinterpret_cast<const uint8_t*>(L.c2.tc.w_pair[P2][g.ctas - 1][vk]);
+    a.w2 = reinterpret_cast<const uint8_t*>(g.s2d ? L.c2.tc.w_s2d[P2][g.ctas - 1] : L.c2.tc.w_pair[P2][g.ctas - 1][vk]);
     a.w_half_stride = L.c1.tc.half_stride[P][vk];
-    a.w2_half_stride = L.c2.tc.half_stride[P2][vk];
+    a.w2_half_stride = g.s2d ? L.c2.tc.s2d_half_stride[P2] : L.c2.tc.half_stride[P2][vk];
+    a.s2d = g.s2d; a.k2 = g.k2; a.tap_group2 = g.G2; a.w_stage_bytes = (unsigned)g.stage;
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
@@ -604,8 +639,8 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     const double bytes = (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
                          (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     if (env_int("HFG_TC_VERBOSE", 0))
-        fprintf(stderr, "[pair] N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d\n",
-                a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles);
+        fprintf(stderr, "[pair] N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
+                a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
     h->prof_begin(st, label, flops, bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
