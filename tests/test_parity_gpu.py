@@ -535,3 +535,52 @@ def test_fp32_frames_last_with_more_mels_than_channels():
         wav = gen.forward_frames_last(x)
     torch.cuda.synchronize()
     assert float(np.abs(wav.cpu().numpy() - ref).max()) <= 2e-6
+
+
+def test_fp16_mode_saturates_instead_of_overflowing():
+    """The fp16 modes (HFG_MODE_FP16, and the fp16 intermediate of the tf32 mode) convert with saturation at +-65504:
+    weights scaled until the activations leave the fp16 range must still give a finite waveform in [-1, 1] that
+    agrees with the oracle wherever tanh has saturated -- never inf or NaN."""
+    import oracle
+    cfg = synth.DEFAULT_CONFIG
+    sd = synth.make_weights(cfg, 12, gain=4.0)                        # stage-3 activations reach ~1e6, far beyond 65504
+    mel = synth.make_mel(13, 1, 80, 24)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    assert np.abs(ref).max() == 1.0
+    for mode in ("fp16", "tf32"):
+        wav = run(make_gen(cfg, sd, mode), mel)
+        assert np.isfinite(wav).all() and np.abs(wav).max() <= 1.0
+        strong = np.abs(ref) > 0.999
+        agree = float(np.mean(np.sign(wav[strong]) == np.sign(ref[strong])))
+        print(f"overflowing weights[{mode}]: {strong.mean():.2%} of samples saturated in the reference, sign agreement {agree:.4f}")
+        assert agree > 0.6                            # clamped activations still point the same way most of the time
+
+
+def test_forward_lengths_c_abi_errors():
+    """hfg_forward_lengths through the raw C ABI: null lengths, a halo below the receptive radius and an undersized
+    workspace are refused with the documented codes; the host-only hfg_receptive_radius agrees with the module."""
+    cfg = _capi.make_config(**synth.DEFAULT_CONFIG)
+    assert _capi.receptive_radius(cfg) == 13
+    h = _capi.Handle(cfg)
+    for k, v in synth.make_weights(synth.DEFAULT_CONFIG, 1).items():
+        h.set_weight(k, v.ctypes.data, v.shape)
+    h.commit()
+    B, T = 2, 40
+    need = h.workspace_bytes(B, T, _capi.MODE_BF16)
+    mel = torch.zeros(B, 80, T, device="cuda:0")
+    wav = torch.empty(B, 1, T * 256, device="cuda:0")
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda:0")
+    lens = torch.tensor([40, 7], dtype=torch.int32, device="cuda:0")
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward_lengths(mel.data_ptr(), 0, 14, B, T, wav.data_ptr(), ws.data_ptr(), need, _capi.MODE_BF16, 0)
+    assert e.value.code == _capi.ERR_INVALID
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward_lengths(mel.data_ptr(), lens.data_ptr(), 12, B, T, wav.data_ptr(), ws.data_ptr(), need, _capi.MODE_BF16, 0)
+    assert e.value.code == _capi.ERR_INVALID and "receptive radius" in str(e.value)
+    with pytest.raises(_capi.HfgError) as e:
+        h.forward_lengths(mel.data_ptr(), lens.data_ptr(), 14, B, T, wav.data_ptr(), ws.data_ptr(), need - 256, _capi.MODE_BF16, 0)
+    assert e.value.code == _capi.ERR_WORKSPACE
+    h.forward_lengths(mel.data_ptr(), lens.data_ptr(), 14, B, T, wav.data_ptr(), ws.data_ptr(), need, _capi.MODE_BF16, 0)
+    torch.cuda.synchronize()
+    assert float(wav[1, :, 7 * 256:].abs().max()) == 0.0 and bool(torch.isfinite(wav).all())
+    h.close()
