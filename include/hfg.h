@@ -14,7 +14,9 @@
  *     throws across the ABI; hfg_last_error() gives the message of the last
  *     failure on that handle;
  *   - a handle belongs to the CUDA device that was current in hfg_create and is
- *     not thread-safe (one handle per GPU, as one process drives one GPU);
+ *     not thread-safe (one handle per GPU, as one process drives one GPU); it owns one
+ *     set of internal side streams and events, so calls on one handle must be issued on
+ *     one caller stream at a time (a second handle overlaps independent batches);
  *   - device pointers are plain CUDA device pointers owned by the caller
  *     (PyTorch allocates them); `stream` is a cudaStream_t passed as void*;
  *   - hfg_forward is asynchronous on `stream`.
@@ -167,7 +169,8 @@ int hfg_forward_host_ex(hfg_handle* h, const float* mel_host, int32_t batch, int
  * slot's waveform has landed.  The copies of one submission overlap the kernels of its neighbours, so a steady
  * stream of batches runs at the device rate.  Both host buffers MUST be page-locked and must stay untouched until
  * wait(slot) returns; a slot must be waited for before it is submitted again (HFG_ERR_STATE otherwise).  Results are
- * identical to hfg_forward_host. */
+ * identical to hfg_forward_host.  The blocking and the streaming calls share the handle's compute stream and workspace:
+ * drain the slots (wait) before mixing in hfg_forward_host* calls or re-committing weights. */
 int hfg_forward_host_submit(hfg_handle* h, int32_t slot, const float* mel_host, int32_t batch, int32_t frames,
                             float* wav_host, int32_t mode);
 int hfg_forward_host_wait(hfg_handle* h, int32_t slot);

@@ -237,17 +237,15 @@ ard_attention(const float* __restrict__ q, int ldq, const float* __restrict__ k_
     }
 }
 
-// frame -> mel[b, step, :]; then the step counter advances (last kernel of a step)
+// frame -> mel[b, step, :].  The step counter is advanced by the following one-thread launch (ard_advance), the last
+// node of a step, so that no kernel of the step ever races with the increment.
 __global__ void ard_store_frame(const float* __restrict__ frame, float* __restrict__ mel, int B, int n_mels, int max_len,
-                                int* __restrict__ step) {
+                                const int* __restrict__ step) {
     const int t = *step;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * n_mels; e += gridDim.x * blockDim.x) {
         const int b = e / n_mels, c = e - b * n_mels;
         mel[((size_t)b * max_len + t) * n_mels + c] = frame[e];
     }
-    __threadfence();
-    // every block has read *step before any block can have finished; the single increment happens in a
-    // following 1-thread launch (ard_advance) to keep this kernel free of inter-block ordering
 }
 __global__ void ard_advance(int* step) { *step += 1; }
 

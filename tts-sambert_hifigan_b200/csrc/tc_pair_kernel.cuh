@@ -66,6 +66,8 @@ struct TcPairArgs {
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
     int epi_sleep_ns; // epilogue warps: longest sleep between polls of a barrier (0 = spin)
+    int pdl;          // launched with programmatic stream serialisation: the prologue above griddepcontrol.wait (barrier
+                      // init, TMEM allocation, bias staging -- nothing an earlier kernel writes) overlaps the predecessor's tail
     int dbg;          // HFG_TUNING builds only -- timing experiments (results are wrong): 1 = no weight copies, 2 = no activation copies, 4 = tap shifts of 8 rows (128-byte aligned operand reads), 8 = epilogue warps only keep the barrier protocol, 16 = no MMAs issued
     int tiles_per_batch, n_tiles;
     // variable-length batches: rows of this stage that utterance b needs (valid frames + receptive halo, scaled to
@@ -179,6 +181,12 @@ tc_pair_kernel(const TcPairArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t acc1 = tmem_base, acc2 = tmem_base + (uint32_t)(MT * N);
+    if (a.pdl) {
+        // let the next launch of this stream place its CTAs as ours retire, then wait until everything this
+        // kernel depends on (the previous launch of the stream and all it waited for) has completed and is visible
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     // tile schedule: cluster c takes tile pairs c, c + n_clusters, ...; CTA `rank` runs tile 2*pair + rank.
     // An odd tail tile is duplicated on the peer (same coordinates, stores suppressed) so both CTAs
     // stay in lockstep on the shared weight ring.

@@ -596,6 +596,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
+    a.pdl = env_int("HFG_TC_PDL", 0);
     a.dbg = env_int("HFG_TC_DBG", 0);
     a.b1 = L.c1.bias; a.b2 = L.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
@@ -647,11 +648,13 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     cfg.blockDim = dim3(kPairThreads);
     cfg.dynamicSmemBytes = g.smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = a.pdl ? 2 : 1;
     check_cuda(cudaLaunchKernelEx(&cfg, fn, a), "tc_pair_kernel launch");
     h->prof_end(st);
     check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
