@@ -184,3 +184,46 @@ def test_config5_batch64_end_to_end():
         for i in range(B):                                 # length-aware run: valid region identical
             n = int(lens[i]) * 256
             assert torch.equal(rag[i, :, :n], wav[i, :, :n])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [
+    dict(d_model=64, n_mels=20, n_layers=2, n_heads=4, d_ff=96, B=70, T=9, max_len=12),     # head_dim 16, two row tiles, max_len > frames
+    dict(d_model=128, n_mels=80, n_layers=1, n_heads=2, d_ff=520, B=3, T=33, max_len=5),    # head_dim 64, split-K with a ragged last chunk, max_len < frames
+    dict(d_model=128, n_mels=16, n_layers=1, n_heads=1, d_ff=64, B=2, T=4, max_len=4),      # head_dim 128
+])
+def test_cuda_decoder_other_geometries_match_oracle(geom):
+    """Geometries the reference never instantiates (its defaults are fixed in models/acoustic_model.py:112-114) against
+    the KV-cached oracle, which is itself pinned to the reference at the default geometry."""
+    import oracle.ar_decoder as oard
+    import tts_sambert_hifigan_b200 as pkg
+    cfg = {k: geom[k] for k in ("d_model", "n_mels", "n_layers", "n_heads", "d_ff")}
+    sd = {k: torch.from_numpy(v) for k, v in synth.make_ard_weights(cfg, 410).items()}
+    sd["pos_encoding.pe"] = oard.positional_encoding(5000, cfg["d_model"]).unsqueeze(0)
+    hvar = torch.from_numpy(synth.normal(411, (geom["B"], geom["T"], cfg["d_model"])))
+    with torch.no_grad():
+        want = oard.decode(sd, hvar, cfg["n_layers"], cfg["n_heads"], max_len=geom["max_len"])
+    dec = pkg.PNCAARDecoder(**cfg, verbose=False).eval().to("cuda:0")
+    dec.load_state_dict(sd)
+    with torch.no_grad():
+        got = dec(hvar.to("cuda:0"), max_len=geom["max_len"])
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (geom["B"], geom["max_len"], cfg["n_mels"])
+    err = float((got.cpu() - want).abs().max())
+    print(f"decoder {cfg}: max-abs vs oracle {err:.3e} (peak {float(want.abs().max()):.2f})")
+    assert err <= TOL_MEL
+
+
+@pytest.mark.gpu
+def test_cuda_decoder_rejects_bad_arguments():
+    import tts_sambert_hifigan_b200 as pkg
+    from tts_sambert_hifigan_b200 import ar_decoder
+    with pytest.raises(_capi.HfgError) as e:               # head_dim 24 is not a supported tile
+        ar_decoder._Handle(96, 80, 1, 4, 64, 5000)
+    assert e.value.code == _capi.ERR_UNSUPPORTED
+    dec = pkg.PNCAARDecoder(d_model=64, n_mels=8, n_layers=1, n_heads=2, d_ff=32, verbose=False).eval().to("cuda:0")
+    with pytest.raises(RuntimeError):
+        dec(torch.zeros(1, 4, 65, device="cuda:0"))
+    with pytest.raises(_capi.HfgError) as e:               # beyond the positional-encoding table (reference: 5000 rows)
+        dec(torch.zeros(1, 4, 64, device="cuda:0"), max_len=5001)
+    assert e.value.code == _capi.ERR_INVALID

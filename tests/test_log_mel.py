@@ -61,3 +61,31 @@ def test_cuda_log_mel_matches_oracle_and_reference_value(manifest):
     assert lm.shape == ref.shape and np.abs(lm - ref).max() <= 5e-5
     with pytest.raises(_capi.HfgError):
         metrics.log_mel(torch.zeros(1, 1, 100).cuda())      # shorter than the reflect padding
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", [
+    dict(sample_rate=16000, n_fft=512, hop_length=128, win_length=512, n_mels=40, fmin=50.0, fmax=7600.0),
+    dict(sample_rate=22050, n_fft=2048, hop_length=512, win_length=2048, n_mels=128, fmin=0.0, fmax=11025.0),
+])
+def test_cuda_log_mel_other_configurations(cfg):
+    """The kernel is parametrised like configs/config.yaml's `audio:` section; other FFT sizes / filterbanks against
+    the float64 oracle (hfg_mel_create through the raw C ABI)."""
+    lib = _capi.load()
+    c = metrics._MelConfig(cfg["sample_rate"], cfg["n_fft"], cfg["hop_length"], cfg["win_length"], cfg["n_mels"],
+                           cfg["fmin"], cfg["fmax"])
+    h = ctypes.c_void_p()
+    assert lib.hfg_mel_create(ctypes.byref(c), ctypes.byref(h)) == 0
+    w = (synth.normal(91, (2, 9000)) * 0.05).astype(np.float32)
+    x = torch.from_numpy(w).cuda()
+    frames = 9000 // cfg["hop_length"] + 1
+    out = torch.empty((2, cfg["n_mels"], frames), dtype=torch.float32, device="cuda")
+    assert lib.hfg_log_mel(h, x.data_ptr(), 2, 9000, out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    ref = olm.log_mel(w, cfg)
+    err = float(np.abs(out.cpu().numpy() - ref).max())
+    print(f"log-mel n_fft {cfg['n_fft']} n_mels {cfg['n_mels']}: max-abs vs float64 oracle {err:.3e}")
+    assert ref.shape == tuple(out.shape) and err <= 1e-4
+    bad = metrics._MelConfig(22050, 1000, 256, 1000, 80, 0.0, 8000.0)          # n_fft not a power of two
+    assert lib.hfg_mel_create(ctypes.byref(bad), ctypes.byref(ctypes.c_void_p())) == _capi.ERR_INVALID
+    lib.hfg_mel_destroy(h)

@@ -584,3 +584,28 @@ def test_forward_lengths_c_abi_errors():
     torch.cuda.synchronize()
     assert float(wav[1, :, 7 * 256:].abs().max()) == 0.0 and bool(torch.isfinite(wav).all())
     h.close()
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_ragged_batch_on_odd_upsample_geometry(manifest, mode):
+    """Per-utterance lengths on a geometry whose stages do not scale by an integer (k - u odd: T_out = u T + 1 on two
+    stages, receptive radius derived, not 13): the device-side length table must follow the same recurrence as the
+    layers.  Valid region against the full-length run, bit for bit."""
+    cfg, sd, _ = case_inputs(manifest, "odd_upsample_b1_t20")
+    gen = make_gen(cfg, sd, mode)
+    radius = gen.receptive_radius
+    lens = [61, 9, 33, 1, 48]
+    mel = torch.from_numpy(synth.make_mel(17, len(lens), cfg["n_mels"], max(lens))).to("cuda:0")
+    with torch.no_grad():
+        full = gen(mel)
+        for ws in gen._workspaces.values():
+            ws.fill_(0xFF)
+        rag = gen.forward_ragged(mel, lens)
+    torch.cuda.synchronize()
+    assert rag.shape == full.shape and bool(torch.isfinite(rag).all())
+    for i, n in enumerate(lens):
+        valid = synth.out_length(cfg, n)                    # samples the first n frames produce in this geometry
+        # every sample of the first n frames' output has its receptive field inside the first n + halo frames
+        assert torch.equal(rag[i, :, :valid], full[i, :, :valid]), (i, radius)
+        if n < max(lens):
+            assert float(rag[i, :, valid:].abs().max()) == 0.0
