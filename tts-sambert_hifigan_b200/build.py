@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    "--threads", "4",           # the .cu files of one library compile side by side
 ]
 
 
@@ -55,10 +56,18 @@ def _compile(lib: str, extra, verbose: bool):
 
 def build(force: bool = False, verbose: bool = False, tuning: bool = True) -> str:
     """Production library, and (tuning=True) the instrumented build next to it."""
+    jobs = []
     if force or is_stale(LIB):
-        _compile(LIB, [], verbose)
+        jobs.append((LIB, [], verbose))
     if tuning and (force or is_stale(LIB_TUNING)):
-        _compile(LIB_TUNING, ["-DHFG_TUNING"], False)
+        jobs.append((LIB_TUNING, ["-DHFG_TUNING"], False))
+    if len(jobs) > 1:                        # the two libraries are independent: build them at the same time
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(len(jobs)) as ex:
+            for f in [ex.submit(_compile, *j) for j in jobs]:
+                f.result()
+    elif jobs:
+        _compile(*jobs[0])
     return LIB
 
 
