@@ -65,7 +65,11 @@ typedef enum hfg_status {
  * (reference tests/test_hifigan_integration.py:50). */
 typedef enum hfg_mode {
     HFG_MODE_FP32 = 0,  /* fp32 FFMA kernels, fp32 activations: strict parity mode      */
-    HFG_MODE_TF32 = 1,  /* tcgen05 kind::tf32, fp32 activations (parity <= 1e-3)          */
+    HFG_MODE_TF32 = 1,  /* TF32-class arithmetic on tensor cores: 10-bit-mantissa operands, fp32 accumulate,
+                           residual stream kept to >= 22 mantissa bits (parity <= 1e-3).  Configurations whose
+                           every ResBlock pair fits the fused kernel (the default one does) run it on fp16
+                           operand planes -- the same 10-bit mantissa, rounded to nearest -- with the residual
+                           stream stored as an fp16 pair hi + lo; others use tcgen05 kind::tf32 on fp32 planes */
     HFG_MODE_BF16 = 2,  /* tcgen05 kind::f16 (bf16 operands), bf16 activations, fp32 acc  */
     HFG_MODE_FP16 = 3   /* tcgen05 kind::f16 (fp16 operands), fp16 activations, fp32 acc: tf32's 10-bit
                            mantissa at bf16's MMA rate; conversions saturate at +-65504 (parity <= 1e-3) */

@@ -77,6 +77,9 @@ struct TcConvArgs {
     const float* bias;
     // output / residual planes (operand dtype, chunk layout, same geometry)
     uint8_t* out; const uint8_t* res; long long o_bstride, o_pstride;
+    // "lo" twin of `out` (same geometry), or null: tf32 mode on fp16 operand planes (tc_path.cuh, split plan) -- the
+    // value is stored as the fp16 pair hi = fp16(v) (plane `out`, what the MMAs read) and lo = fp16(v - hi)
+    uint8_t* out_lo;
     // MRF accumulator planes: fp32, 4 channels per 16-byte cell
     float* acc; long long acc_bstride, acc_pstride;   // in bytes
     int acc_mode; float inv_scale;                    // TC_ACC_FINAL: v = (acc + v) / n_resblocks
@@ -407,6 +410,31 @@ __device__ __forceinline__ void load_cells16(const uint8_t* p, long long plane_s
         for (int g = 0; g < 4; ++g) { v[g * 4 + 0] = u[g].x; v[g * 4 + 1] = u[g].y; v[g * 4 + 2] = u[g].z; v[g * 4 + 3] = u[g].w; }
     }
 }
+// fp32 value as an fp16 pair: hi = fp16(v), lo = fp16(v - hi).  hi + lo carries 22 bits of mantissa (absolute floor
+// 3e-8 in fp16's subnormal range); hi alone is the round-to-nearest 10-bit-mantissa operand a tf32 MMA would see.
+// Both conversions saturate, so the pair stays finite whatever v is.
+__device__ __forceinline__ void split16(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack_fp16(v[2 * i], v[2 * i + 1]);
+        float h0, h1;
+        unpack_fp16(h[i], h0, h1);
+        l[i] = pack_fp16(v[2 * i] - h0, v[2 * i + 1] - h1);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// 16 consecutive channels of one row -> two cells of the hi planes and two of the lo planes
+__device__ __forceinline__ void store_split16(uint8_t* hi_p, uint8_t* lo_p, long long plane_stride, const float (&v)[16]) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint4 hi, lo;
+        split16(v + g * 8, hi, lo);
+        *reinterpret_cast<uint4*>(hi_p + g * plane_stride) = hi;
+        *reinterpret_cast<uint4*>(lo_p + g * plane_stride) = lo;
+    }
+}
 __device__ __forceinline__ void load_f32x16(const uint8_t* p, long long plane_stride, float (&v)[16]) {
     float4 u[4];
 #pragma unroll
@@ -649,6 +677,14 @@ tc_conv_kernel(const TcConvArgs a) {
                     if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                        if constexpr (P == PREC_FP16) {
+                            if (a.out_lo) {
+                                store_split16(op + (long long)(ch / CW) * a.o_pstride,
+                                              a.out_lo + (long long)b * a.o_bstride + row_bytes + (long long)(ch / CW) * a.o_pstride,
+                                              a.o_pstride, v);
+                                continue;
+                            }
+                        }
                         store_cells16<P>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
                     }
                 }

@@ -46,6 +46,15 @@ struct TcPairArgs {
     // adds the finished outputs of the other resblocks -- ordinary leaky_relu(x_j) planes with the geometry of
     // `out`, inverted exactly on load -- to its accumulator before conv2, then scales by 1 / n_resblocks.
     const uint8_t* sum_in[HFG_MAX_STAGES - 1]; int n_sum;
+    // LO kernels (tf32 mode on fp16 operand planes, tc_path.cuh "split plan"): the residual stream is stored as the fp16
+    // pair hi + lo (22 mantissa bits).  `a` / `out` are the hi planes -- what the MMAs read --, a_lo / out_lo their lo
+    // twins (same geometry).  The producer copies the lo cells of the tile's own MT * 128 rows into the H-TILE BUFFER,
+    // which is idle between conv2 of tile i (tcgen05.commit -> ACC2_FULL) and epi1 of tile i+1: no extra shared
+    // memory, nothing loaded synchronously; pre2 forms the residual hi + lo from shared memory, and a named barrier
+    // of the epilogue warps separates those reads from epi1's writes of H.  out_lo may be null (the result only
+    // feeds MMAs); out32 (fp32 cells, geometry o32_*) replaces out / out_lo where the result only feeds the MRF sum
+    // or conv_post; sum_in then points at such fp32 planes.
+    const uint8_t* a_lo; uint8_t* out_lo; uint8_t* out32; long long o32_bstride, o32_pstride;
     int N;            // channels (C_in = C_out = N)
     int n_chunks;     // N / CW
     int MT;           // 128-row sub-tiles per tile
@@ -110,7 +119,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // CTAS = 2: a cluster of two CTAs runs two adjacent tiles in lockstep; the leader CTA issues
 // tcgen05.mma.cta_group::2 (M = 256) for both, each CTA stages only its half of every weight tile
 // (half the L2->smem weight traffic and half the B-operand smem reads per SM).
-template <int P, int P2, int MINB, int CTAS>
+// LO = true (P = P2 = PREC_FP16): operands are the fp16 hi planes, the residual stream is the pair hi + lo -- the
+// arithmetic of the tf32 mode (10-bit-mantissa operands, fp32 accumulate, >= 22-bit residual stream) at the fp16
+// mode's MMA rate and shared-memory operand bytes, with the fp32 planes' HBM bytes.
+template <int P, int P2, int MINB, int CTAS, bool LO = false>
 __global__ void __launch_bounds__(kPairThreads, MINB)
 tc_pair_kernel(const TcPairArgs a) {
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
@@ -129,6 +141,7 @@ tc_pair_kernel(const TcPairArgs a) {
     const int N2 = N * PP, NB2 = N2 / CTAS, MT2 = MT / PP, k2 = a.k2;
     const int n_chunks2 = (N / CW2) * PP;             // cells per row of the H tile (conv2's K extent)
     const int n_kb2 = (n_chunks2 + KBC - 1) / KBC;
+    const int RL = MT * 128;                          // LO kernels: lo rows per chunk, parked in the H-tile buffer
     const uint32_t a_stage_bytes = (uint32_t)R1 * nck_max * 16;
     const int G = a.tap_group, G2 = a.tap_group2;
     const uint32_t w_stage_bytes = a.w_stage_bytes;
@@ -144,8 +157,8 @@ tc_pair_kernel(const TcPairArgs a) {
     auto W_FULL = [&](int i) { return bar0 + 8u * (2 * kPairMaxSA + i); };
     auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kPairMaxSA + kMaxSW + i); };
     const uint32_t ACC1_FULL = bar0 + 8u * (2 * kPairMaxSA + 2 * kMaxSW);
-    const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairMaxSA + 2 * kMaxSW + 3);
+    const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16, LO_FULL = ACC1_FULL + 24;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairMaxSA + 2 * kMaxSW + 4);
 
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * N) ncols <<= 1;
@@ -159,6 +172,7 @@ tc_pair_kernel(const TcPairArgs a) {
         mbar_init(ACC1_FULL, 1);
         mbar_init(H_READY, kPairEpiWarps * CTAS);
         mbar_init(ACC2_FULL, 1);
+        mbar_init(LO_FULL, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -227,10 +241,29 @@ tc_pair_kernel(const TcPairArgs a) {
         int a_sc = next_live(sched0), a_kb = 0;                  // next A block: schedule slot, K block
         int w_sc = a_sc, w_conv = 0, w_kb = 0, w_g = 0;          // next W stage
         int a_t = 0, w_t = 0;                                    // ordinals of those slots among this CTA's live ones
+        int l_sc = LO ? a_sc : n_sched, l_t = 0;                 // LO kernels: next tile whose lo rows go into the H-tile buffer
         uint32_t idle = 0;
         long long t_idle0 = 0;
-        while (a_sc < n_sched || w_sc < n_sched) {
+        while (a_sc < n_sched || w_sc < n_sched || l_sc < n_sched) {
             bool did = false;
+            if constexpr (LO) {
+                // the H-tile buffer is free once conv2 of the previous tile has completed (its tcgen05.commit on ACC2_FULL)
+                if (l_sc < n_sched && (l_t == 0 || mbar_test(ACC2_FULL, (uint32_t)((l_t - 1) & 1)))) {
+                    if (leader) {
+                        const int tile = tile_of(l_sc);
+                        const uint8_t* lb = a.a_lo + (long long)(tile / a.tiles_per_batch) * a.a_bstride +
+                                            (long long)(kPadL + (tile % a.tiles_per_batch) * a.TO) * 16;
+                        mbar_expect_tx(LO_FULL, (uint32_t)n_chunks * RL * 16);
+                        const uint32_t dst = smem_u32(sH);
+                        for (int c = 0; c < n_chunks; ++c)
+                            bulk_g2s(dst + (uint32_t)c * RL * 16, lb + (long long)c * a.a_pstride, (uint32_t)RL * 16, LO_FULL);
+                    }
+                    __syncwarp();
+                    ++l_t;
+                    l_sc = next_live(l_sc + sched_step);
+                    did = true;
+                }
+            }
             if (a_sc < n_sched && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int nck = (n_chunks - KBC * a_kb) < KBC ? (n_chunks - KBC * a_kb) : KBC;
                 if (a_kb == 0) HFG_TL(0, a_t);
@@ -409,6 +442,7 @@ tc_pair_kernel(const TcPairArgs a) {
             const int b = tile / a.tiles_per_batch;
             const int t0 = (tile % a.tiles_per_batch) * a.TO;
             // ---------- pre2: acc2 <- x + b2 (+ partial MRF sum), per K block as it lands ----------
+            if constexpr (LO) mbar_wait_sleep(LO_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
             for (int kb = 0; kb < n_kb; ++kb) {
                 const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
                 mbar_wait_sleep(A_FULL(sa_i), sa_ph, (uint32_t)a.epi_sleep_ns);
@@ -423,7 +457,9 @@ tc_pair_kernel(const TcPairArgs a) {
                     const uint8_t* accp = reinterpret_cast<const uint8_t*>(a.acc) + (long long)b * a.acc_bstride +
                                           (long long)(kPadL + t) * 16;
                     const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2 + pp * N + kb * KBC * CW);
-                    const uint8_t* sump = a.n_sum ? a.sum_in[0] + (long long)b * a.o_bstride + (long long)(kPadL + t) * 16 : nullptr;
+                    const long long sum_b = LO ? a.o32_bstride : a.o_bstride, sum_p = LO ? a.o32_pstride : a.o_pstride;
+                    const uint8_t* sump = a.n_sum ? a.sum_in[0] + (long long)b * sum_b + (long long)(kPadL + t) * 16 : nullptr;
+                    const uint8_t* lp = sH + (size_t)(kb * KBC) * RL * 16 + (size_t)lr * 16;   // lo twin of row lr (LO kernels)
                     for (int c16 = 0; c16 < nck * CW; c16 += 16) {              // 16 columns at a time
                         const int col = kb * KBC * CW + c16;                    // channel; acc2 column = pp * N + col
                         // column ownership must match epi2 (32-column groups of acc2 alternate between the two
@@ -433,6 +469,11 @@ tc_pair_kernel(const TcPairArgs a) {
                         float v[16];
                         load_cells16<P>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
                         float prev[16];
+                        if constexpr (LO) {
+                            load_cells16<P>(lp + (long long)(c16 / CW) * ((long long)RL * 16), (long long)RL * 16, prev);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) v[i] += prev[i];
+                        }
                         if (add_prev && a.n_sum == 0) load_f32x16(accp + (long long)(col / 4) * a.acc_pstride, a.acc_pstride, prev);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = lrelu_inv(v[i], inv_slope);
@@ -443,7 +484,8 @@ tc_pair_kernel(const TcPairArgs a) {
                         }
                         if (add_prev && a.n_sum > 0) {                          // + rb_j(x) for the other resblocks
                             for (int s = 0; s < a.n_sum; ++s) {
-                                load_cells16<P>(sump + (a.sum_in[s] - a.sum_in[0]) + (long long)(col / CW) * a.o_pstride, a.o_pstride, prev);
+                                if constexpr (LO) load_f32x16(sump + (a.sum_in[s] - a.sum_in[0]) + (long long)(col / 4) * sum_p, sum_p, prev);
+                                else load_cells16<P>(sump + (a.sum_in[s] - a.sum_in[0]) + (long long)(col / CW) * sum_p, sum_p, prev);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) v[i] += lrelu_inv(prev[i], inv_slope);
                             }
@@ -457,6 +499,8 @@ tc_pair_kernel(const TcPairArgs a) {
                 if (lane == 0) mbar_arrive(A_EMPTY(sa_i));
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
             }
+            // LO kernels: every epilogue warp has read its lo cells before any of them overwrites the buffer with H
+            if constexpr (LO) asm volatile("bar.sync 1, %0;" ::"n"(32 * kPairEpiWarps) : "memory");
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
             if (e == 0) HFG_TL(6, it);
             mbar_wait_sleep(ACC1_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
@@ -539,7 +583,18 @@ tc_pair_kernel(const TcPairArgs a) {
                             }
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
-                            store_cells16<P>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
+                            if constexpr (LO) {
+                                if (a.out32)
+                                    store_f32x16(a.out32 + (long long)b * a.o32_bstride + row_bytes + (long long)(cc / 4) * a.o32_pstride,
+                                                 a.o32_pstride, v);
+                                else if (a.out_lo)
+                                    store_split16(op + (long long)(cc / CW) * a.o_pstride,
+                                                  a.out_lo + (long long)b * a.o_bstride + row_bytes + (long long)(cc / CW) * a.o_pstride,
+                                                  a.o_pstride, v);
+                                else store_cells16<P>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
+                            } else {
+                                store_cells16<P>(op + (long long)(cc / CW) * a.o_pstride, a.o_pstride, v);
+                            }
                         }
                     }
                 }

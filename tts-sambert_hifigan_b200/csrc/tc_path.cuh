@@ -248,20 +248,55 @@ static inline bool tc_stage_sum_planes(const hfg_handle* h, size_t i, int n_chun
     return tc_pair_geometry(h, mrf.back().back(), n_chunks, prec).ok;
 }
 
+// The tf32 mode on fp16 operand planes ("split plan").  kind::tf32 reads 10 mantissa bits of each fp32 operand, so an
+// MMA fed from fp32 planes moves 4 bytes per element through L2 and -- what bounds the narrow stages -- the 64 B/clk
+// shared-memory operand read to use 10 + 8 bits of them, at half the kind::f16 rate.  In the split plan an activation
+// of the residual stream is stored as TWO fp16 planes, hi = fp16(v) and lo = fp16(v - hi):
+//   * hi is the round-to-nearest 10-bit-mantissa operand (tf32 truncates): every MMA reads hi planes only, at the
+//     fp16 mode's rate and operand bytes;
+//   * hi + lo carries 22 mantissa bits (absolute floor 3e-8): the residual x of a fused pair is formed from both --
+//     the producer copies the lo cells of the tile's own rows into the (then idle) H-tile buffer, so nothing is
+//     loaded synchronously and no shared memory is added -- and the pair writes both halves of its result;
+//   * HBM bytes per element are those of the fp32 planes (2 + 2 read, 2 + 2 written).
+// Planes that only feed MMAs (mel, conv_pre output, an MRF output followed by an upsampler) have no lo twin; the
+// finished resblock outputs that only feed the MRF sum, and the last MRF output (conv_post), are plain fp32 planes.
+// Used when every pair of the configuration fits the fused kernel (else the fp32-plane kind::tf32 path).
+static inline bool tc_tf32_mixed(const hfg_handle* h) {
+    if (!env_int("HFG_TC_TF32_MIXED", 1)) return false;
+    if (h->post_cin % 8 != 0) return false;
+    for (size_t i = 0; i < h->ups.size(); ++i) {
+        const int C = h->ups[i].cout;
+        if (C % 8 != 0) return false;
+        for (auto& rb : h->mrfs[i])
+            for (auto& P : rb)
+                if (!tc_pair_geometry(h, P, C / 8, PREC_FP16).ok) return false;
+        if (h->mrfs[i].size() > 1 && !tc_stage_sum_planes(h, i, C / 8, PREC_FP16)) return false;
+    }
+    return true;
+}
+
 struct TcPlan {
+    bool mixed = false;                     // tf32 mode on fp16 hi + lo planes (tc_tf32_mixed)
     TcPlane mel, pre;                       // packed mel, conv_pre output
     // per stage: X = upsampler output, Y = MRF output and, per resblock (they run concurrently), two ping-pong
     // planes R, H.  Only where a pair does not fit the fused kernel: a scratch S for its intermediate, and an
     // fp32 running-sum plane ACC if that pair is the one that forms the MRF sum.
-    struct Stage { TcPlane X, Y, ACC; bool sum_planes = false; struct { TcPlane R, H, S; bool fused = true; } rb[HFG_MAX_STAGES]; } st[HFG_MAX_STAGES];
+    // split plan: Xl / Rl / Hl = lo twins of X / R / H (same geometry); F32 = finished output of a resblock that
+    // only feeds the MRF sum (fp32); the MRF output is Y (hi only) where an upsampler follows and Y32 (fp32) in
+    // the last stage, which conv_post reads
+    struct Stage {
+        TcPlane X, Y, ACC, Xl, Y32; bool sum_planes = false;
+        struct { TcPlane R, H, S, Rl, Hl, F32; bool fused = true; } rb[HFG_MAX_STAGES];
+    } st[HFG_MAX_STAGES];
     size_t lens_off = 0;                    // int32 [(num_upsamples + 2)][B]: per-utterance row counts (tc_len_table)
     size_t total = 0;
 };
 
 static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
-    const int prec = tc_prec_of_mode(mode);
-    const int cw = prec == PREC_TF32 ? 4 : 8;
     TcPlan p;
+    p.mixed = mode == HFG_MODE_TF32 && tc_tf32_mixed(h);
+    const int prec = p.mixed ? PREC_FP16 : tc_prec_of_mode(mode);
+    const int cw = prec == PREC_TF32 ? 4 : 8;
     size_t cur = 0;
     p.mel = tc_plane(B, h->cfg.n_mels, T, cw, cur);
     p.pre = tc_plane(B, h->cfg.upsample_initial_channel, T, cw, cur);
@@ -270,8 +305,11 @@ static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
         const UpLayer& U = h->ups[i];
         t = (t - 1) * U.u - 2 * U.p + U.k;
         auto& S = p.st[i];
+        const bool last_stage = i + 1 == h->ups.size();
         S.X = tc_plane(B, U.cout, t, cw, cur);
-        S.Y = tc_plane(B, U.cout, t, cw, cur);
+        if (p.mixed) S.Xl = tc_plane(B, U.cout, t, cw, cur);
+        if (p.mixed && last_stage) S.Y32 = tc_plane(B, U.cout, t, 4, cur);
+        else S.Y = tc_plane(B, U.cout, t, cw, cur);
         const int n_rb = h->cfg.num_resblocks;
         S.sum_planes = tc_stage_sum_planes(h, i, S.X.nchunks, prec);
         for (int j = 0; j < n_rb; ++j) {
@@ -280,10 +318,15 @@ static inline TcPlan tc_plan(const hfg_handle* h, int B, int T, int mode) {
             for (auto& P : rb) fused = fused && tc_pair_geometry(h, P, S.X.nchunks, prec).ok;
             S.rb[j].fused = fused;
             // R: output of pair 0 (or, with sum planes, the finished output of a one-pair resblock); H: its partner
-            const bool need_r = rb.size() > 1 || (S.sum_planes && j + 1 < n_rb);
-            const bool need_h = rb.size() > 2 || (S.sum_planes && j + 1 < n_rb && rb.size() > 1);
+            // (split plan: the finished outputs go to F32 instead, so R / H only hold intermediate results)
+            const bool fin_rh = S.sum_planes && j + 1 < n_rb && !p.mixed;
+            const bool need_r = rb.size() > 1 || fin_rh;
+            const bool need_h = rb.size() > 2 || (fin_rh && rb.size() > 1);
             if (need_r) S.rb[j].R = tc_plane(B, U.cout, t, cw, cur);
             if (need_h) S.rb[j].H = tc_plane(B, U.cout, t, cw, cur);
+            if (need_r && p.mixed) S.rb[j].Rl = tc_plane(B, U.cout, t, cw, cur);
+            if (need_h && p.mixed) S.rb[j].Hl = tc_plane(B, U.cout, t, cw, cur);
+            if (p.mixed && j + 1 < n_rb) S.rb[j].F32 = tc_plane(B, U.cout, t, 4, cur);
             if (!fused) S.rb[j].S = tc_plane(B, U.cout, t, cw, cur);
         }
         if (!S.sum_planes && n_rb > 1) S.ACC = tc_plane(B, U.cout, t, 4, cur);          // fp32 accumulator cells
@@ -576,13 +619,18 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
     return best;
 }
 
-template <int P>
+// LO: the kernel variant of the split plan -- in_lo / out_lo are the lo twins of in / out (same geometry; out_lo may
+// be null), out32 (fp32 cells, geometry o32_b / o32_p) replaces out where the result only feeds the MRF sum or
+// conv_post; sum_in then holds such fp32 planes
+template <int P, bool LO = false>
 static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, const PairGeom& g,
                            const uint8_t* in, long long in_b, long long in_p, int n_chunks,
                            uint8_t* out, long long out_b, long long out_p,
                            float* acc, long long acc_b, long long acc_p, int acc_mode, float div,
                            const uint8_t* const* sum_in, int n_sum, const int* len_rows,
-                           int B, int T, const char* label) {
+                           int B, int T, const char* label,
+                           const uint8_t* in_lo = nullptr, uint8_t* out_lo = nullptr, uint8_t* out32 = nullptr,
+                           long long o32_b = 0, long long o32_p = 0) {
     constexpr int ESZ = Prec<P>::ESZ;
     TcPairArgs a{};
     a.a = in; a.a_bstride = in_b; a.a_pstride = in_p;
@@ -600,6 +648,10 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.dbg = env_int("HFG_TC_DBG", 0);
     a.b1 = L.c1.bias; a.b2 = L.c2.bias;
     a.out = out; a.o_bstride = out_b; a.o_pstride = out_p;
+    a.a_lo = in_lo; a.out_lo = out_lo; a.out32 = out32; a.o32_bstride = o32_b; a.o32_pstride = o32_p;
+    // the lo rows of a tile (MT * 128 per chunk) are parked in the H-tile buffer
+    if (LO && (size_t)g.MT * 128 * n_chunks > (size_t)g.RH * (g.s2d ? 2 : 1) * n_chunks)
+        throw StatusError(HFG_ERR_INVALID, "internal: H-tile buffer smaller than the lo rows");
     a.acc = acc; a.acc_bstride = acc_b; a.acc_pstride = acc_p; a.acc_mode = acc_mode; a.div = div;
     a.n_sum = n_sum;
     for (int s = 0; s < n_sum; ++s) a.sum_in[s] = sum_in[s];
@@ -616,7 +668,11 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     const int ctas = g.ctas;
     using KernelFn = void (*)(TcPairArgs);
     KernelFn fn = nullptr;
-    if (P == PREC_TF32 && P2 == PREC_FP16) {
+    if constexpr (LO) {
+        static_assert(P == PREC_FP16, "the hi + lo variant runs on fp16 operand planes");
+        if (ctas == 2) fn = two ? tc_pair_kernel<P, P, 2, 2, true> : tc_pair_kernel<P, P, 1, 2, true>;
+        else fn = two ? tc_pair_kernel<P, P, 2, 1, true> : tc_pair_kernel<P, P, 1, 1, true>;
+    } else if (P == PREC_TF32 && P2 == PREC_FP16) {
         if (ctas == 2) fn = two ? tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 2> : tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 2>;
         else fn = two ? tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 1> : tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 1>;
     } else {
@@ -624,7 +680,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
         else fn = two ? tc_pair_kernel<P, P, 2, 1> : tc_pair_kernel<P, P, 1, 1>;
     }
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
-    int& regs = h->pair_regs[P == PREC_TF32 && P2 == PREC_FP16 ? 3 : P][two ? 1 : 0][ctas - 1];
+    int& regs = h->pair_regs[LO ? 4 : (P == PREC_TF32 && P2 == PREC_FP16 ? 3 : P)][two ? 1 : 0][ctas - 1];
     if (regs == 0) {
         cudaFuncAttributes fa{};
         check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
@@ -637,11 +693,13 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     const double C = a.N;
     const double flops = 2.0 * 2.0 * C * C * a.k * (double)B * T;
     // algorithmic bytes: the activation in and out once, the other resblocks' outputs (or the fp32 running sum), the weights
-    const double bytes = (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
-                         (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
+    // (split plan: hi + lo in; hi + lo, hi only or fp32 out; fp32 sum planes)
+    const double bytes = LO ? (double)B * T * C * (4.0 + (out32 ? 4.0 : (out_lo ? 4.0 : 2.0)) + 4.0 * n_sum) + 2.0 * ESZ * C * C * a.k
+                             : (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
+                               (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     if (env_int("HFG_TC_VERBOSE", 0))
-        fprintf(stderr, "[pair] N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
-                a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
+        fprintf(stderr, "[pair] lo=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
+                (int)LO, a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
     h->prof_begin(st, label, flops, bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -660,11 +718,13 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     check_cuda(cudaGetLastError(), "tc_pair_kernel launch");
 }
 
-template <int P>
+// MIXED (P = PREC_FP16): the tf32 mode on fp16 hi + lo planes (split plan, tc_tf32_mixed)
+template <int P, bool MIXED = false>
 static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float* wav, char* ws,
                             cudaStream_t st, float* const* stage_out, const int* lengths, int halo) {
     constexpr int ESZ = Prec<P>::ESZ;
-    const TcPlan plan = tc_plan(h, B, T, P == PREC_BF16 ? HFG_MODE_BF16 : (P == PREC_FP16 ? HFG_MODE_FP16 : HFG_MODE_TF32));
+    const TcPlan plan = tc_plan(h, B, T, MIXED ? HFG_MODE_TF32 : (P == PREC_BF16 ? HFG_MODE_BF16 : (P == PREC_FP16 ? HFG_MODE_FP16 : HFG_MODE_TF32)));
+    if (plan.mixed != MIXED) throw StatusError(HFG_ERR_INVALID, "internal: plan / launch-path mismatch");
     const float slope = 0.1f;
     const int n_rb = h->cfg.num_resblocks;
     auto ptr = [&](const TcPlane& p) { return reinterpret_cast<uint8_t*>(ws + p.off); };
@@ -702,7 +762,11 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         // the fused kernel
         add(plan.mel); add(plan.pre);
         for (size_t i = 0; i < h->ups.size(); ++i) {
-            add(plan.st[i].X); add(plan.st[i].Y);
+            add(plan.st[i].X);
+            // split plan: lo twins and F32 planes are read at valid rows only; the last stage's fp32 MRF output is
+            // read through conv_post's halo
+            if (plan.st[i].Y.bytes) add(plan.st[i].Y);
+            if (plan.st[i].Y32.bytes) add(plan.st[i].Y32);
             for (int j = 0; j < n_rb; ++j) {
                 if (h->mrfs[i][j].size() > 1) add(plan.st[i].rb[j].R);
                 if (h->mrfs[i][j].size() > 2) add(plan.st[i].rb[j].H);
@@ -720,10 +784,11 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         h->prof_end(st);
         check_cuda(cudaGetLastError(), "tc_pack_input launch");
     }
-    auto dump = [&](int idx, const TcPlane& p) {
+    auto dump = [&](int idx, const TcPlane& p, bool f32 = false) {
         if (!stage_out || !stage_out[idx]) return;
         dim3 grid((p.T + 127) / 128, p.nchunks, B);
-        tc_unpack_stage<P><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
+        if (f32) tc_unpack_stage<PREC_TF32><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
+        else tc_unpack_stage<P><<<grid, 128, 0, st>>>(ptr(p), stage_out[idx], p.C, p.T, p.bstride, p.pstride, 1.0f / slope);
         check_cuda(cudaGetLastError(), "tc_unpack_stage launch");
     };
     auto conv = [&](cudaStream_t st, const ConvLayer& L, const TcPlane& in, const TcPlane* out, const TcPlane* res,
@@ -779,6 +844,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             a.stack_cout = stack ? U.cout : 0;
             a.bias = U.bias;
             a.out = ptr(S.X); a.res = nullptr; a.o_bstride = S.X.bstride; a.o_pstride = S.X.pstride;
+            if (MIXED) a.out_lo = ptr(S.Xl);
             a.acc_mode = TC_ACC_NONE; a.div = 1.f;
             a.T_out = S.X.T;
             a.n_q = (S.X.T - 1 + U.p) / U.u + 1;
@@ -788,13 +854,13 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
             a.len_rows = lens_of(1 + (int)i);
             const double flops = 2.0 * U.cin * U.cout * U.k * (double)B * cur->T;
             const double bytes = (double)B * ESZ * ((double)U.cin * cur->T + (double)U.cout * S.X.T) +
-                                 (double)ESZ * U.cin * U.cout * U.k;
+                                 (MIXED ? 2.0 * B * U.cout * S.X.T : 0.0) + (double)ESZ * U.cin * U.cout * U.k;
             const std::string ulab = "ups" + std::to_string(i);
             if (!tc_launch_up<P>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes))
                 tc_launch_conv<P>(h, st, a, B, cout_v, ulab.c_str(), flops, bytes);
         }
         h->stage_end(st);
-        dump(1 + 2 * (int)i, S.X);
+        dump(1 + 2 * (int)i, S.X);       // (split plan: the hi half -- the stage hooks are test instrumentation)
 
         h->stage_begin(st, ("mrf" + std::to_string(i)).c_str());
         // MRF (reference :116-131).  The resblocks only meet in the running sum, so resblock j is enqueued on
@@ -861,9 +927,31 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                     const TcPlane* dst = (r == &W.R ? &W.H : &W.R);
                     if (closes || (last && n_rb == 1)) dst = &S.Y;
                     else if (last && !sum_planes) dst = nullptr;
+                    // split plan: lo twin of a plane of this stage
+                    auto twin = [&](const TcPlane* q) -> const TcPlane* {
+                        return q == &S.X ? &S.Xl : (q == &W.R ? &W.Rl : (q == &W.H ? &W.Hl : nullptr));
+                    };
+                    (void)twin;
                     const bool use_acc = mode != TC_ACC_NONE && !sum_planes;
                     const PairGeom g = tc_pair_geometry(h, rb[l], r->nchunks, P);
-                    if (g.ok) {
+                    if (MIXED) {
+                        if constexpr (MIXED) {
+                            // result of this pair: hi + lo where the next pair of the resblock reads it; hi only for
+                            // an MRF output that an upsampler reads; fp32 where only the MRF sum (F32) or
+                            // conv_post (Y32) reads it
+                            const bool is_y = closes || (last && n_rb == 1);
+                            const TcPlane* d32 = !last ? nullptr : (is_y ? (S.Y32.bytes ? &S.Y32 : nullptr) : &W.F32);
+                            const TcPlane& g32 = S.Y32.bytes ? S.Y32 : S.rb[0].F32;     // every fp32 plane of a stage has this geometry
+                            tc_launch_pair<P, true>(h, sj, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
+                                                    d32 ? nullptr : ptr(*dst), S.X.bstride, S.X.pstride,
+                                                    nullptr, 0, 0, mode, (float)n_rb,
+                                                    (sum_planes && closes) ? fin.data() : nullptr, (sum_planes && closes) ? (int)fin.size() : 0,
+                                                    lens_of(1 + (int)i), B, S.X.T, lab.c_str(),
+                                                    ptr(*twin(r)), (!last) ? ptr(*twin(dst)) : nullptr, d32 ? ptr(*d32) : nullptr,
+                                                    g32.bstride, g32.pstride);
+                            if (last && sum_planes && !closes) fin.push_back(ptr(W.F32));
+                        }
+                    } else if (g.ok) {
                         tc_launch_pair<P>(h, sj, rb[l], g, ptr(*r), r->bstride, r->pstride, r->nchunks,
                                           dst ? ptr(*dst) : nullptr, S.X.bstride, S.X.pstride,
                                           use_acc ? reinterpret_cast<float*>(ptr(S.ACC)) : nullptr,
@@ -877,7 +965,7 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
                         conv(sj, rb[l].c2, W.S, dst, r, use_acc ? &S.ACC : nullptr, use_acc ? mode : TC_ACC_NONE, clab.c_str(),
                              lens_of(1 + (int)i));
                     }
-                    if (last && sum_planes && !closes) fin.push_back(ptr(*dst));
+                    if (!MIXED && last && sum_planes && !closes) fin.push_back(ptr(*dst));
                     if (last && n_streams > 1 && j + 1 < n_rb)
                         check_cuda(cudaEventRecord(h->ev_sum[j], sj), "cudaEventRecord(sum)");
                     if (!last) src[j] = dst;
@@ -893,19 +981,25 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
         }
         h->stage_end(st);
         cur = &S.Y;
-        dump(2 + 2 * (int)i, S.Y);
+        if (MIXED && S.Y32.bytes) dump(2 + 2 * (int)i, S.Y32, true); else dump(2 + 2 * (int)i, S.Y);
     }
     // wav = tanh(conv_post(leaky_relu(x)))  (reference :254-256); planes already hold leaky_relu(x)
     {
+        if (MIXED) cur = &plan.st[h->ups.size() - 1].Y32;        // conv_post reads the fp32 residual stream
         const int Tw = cur->T;
         dim3 grid((Tw + kPostTile - 1) / kPostTile, B);
         const size_t post_smem = (size_t)kPostGC * post_col_cells<7>() * 16 + sizeof(float) * h->post_cin * 7;
         h->stage_begin(st, "tail");
         h->prof_begin(st, "conv_post", 2.0 * h->post_cin * 7 * (double)B * Tw,
-                      (double)B * Tw * (ESZ * h->post_cin + 4.0));
-        tc_conv_post_tanh<P, 7><<<grid, kPostThreads, post_smem, st>>>(
-            ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride,
-            lens_of((int)h->ups.size()), lens_of(1 + (int)h->ups.size()));
+                      (double)B * Tw * ((MIXED ? 4 : ESZ) * h->post_cin + 4.0));
+        if (MIXED)
+            tc_conv_post_tanh<PREC_TF32, 7><<<grid, kPostThreads, post_smem, st>>>(
+                ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride,
+                lens_of((int)h->ups.size()), lens_of(1 + (int)h->ups.size()));
+        else
+            tc_conv_post_tanh<P, 7><<<grid, kPostThreads, post_smem, st>>>(
+                ptr(*cur), h->post_w, h->post_b, wav, h->post_cin, Tw, 3, cur->bstride, cur->pstride,
+                lens_of((int)h->ups.size()), lens_of(1 + (int)h->ups.size()));
         h->prof_end(st);
         h->stage_end(st);
         check_cuda(cudaGetLastError(), "tc_conv_post_tanh launch");
@@ -996,6 +1090,7 @@ inline void tc_forward(hfg_handle* h, const float* mel, int B, int T, float* wav
         throw StatusError(HFG_ERR_UNSUPPORTED, "tensor-core modes need an sm_100 device (tcgen05)");
     if (mode == HFG_MODE_BF16) tc_forward_impl<PREC_BF16>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
     else if (mode == HFG_MODE_FP16) tc_forward_impl<PREC_FP16>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
+    else if (tc_tf32_mixed(h)) tc_forward_impl<PREC_FP16, true>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
     else tc_forward_impl<PREC_TF32>(h, mel, B, T, wav, ws, st, stage_out, lengths, halo);
 }
 
@@ -1015,6 +1110,9 @@ inline void configure_kernels(hfg_handle*) {
     };
     big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 1>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 1>);
     big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 2>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 2>);
+    // hi + lo variants (split plan of the tf32 mode)
+    big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 1, true>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 2, 1, true>);
+    big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 2, true>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 2, 2, true>);
     each(std::integral_constant<int, PREC_TF32>{});
     each(std::integral_constant<int, PREC_BF16>{});
     each(std::integral_constant<int, PREC_FP16>{});

@@ -270,6 +270,14 @@ tc_up_kernel(const TcUpArgs ua) {
                         if (a.out) {                             // next layer's leaky_relu, operand dtype
 #pragma unroll
                             for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], slope);
+                            if constexpr (P == PREC_FP16) {
+                                if (a.out_lo) {                  // fp16 hi + lo pair (tf32 mode on fp16 operand planes)
+                                    store_split16(op + (long long)(ch / CW) * a.o_pstride,
+                                                  a.out_lo + (long long)b * a.o_bstride + row_bytes + (long long)(ch / CW) * a.o_pstride,
+                                                  a.o_pstride, v);
+                                    continue;
+                                }
+                            }
                             store_cells16<P>(op + (long long)(ch / CW) * a.o_pstride, a.o_pstride, v);
                         }
                     }

@@ -86,7 +86,8 @@ class HiFiGANGenerator(nn.Module):
 
     Extra keyword (not in the reference): `mode` in {"fp32", "tf32", "bf16", "fp16"} --
     arithmetic of the CUDA path (include/hfg.h hfg_mode); default from
-    $HFG_MODE, else "tf32" (tensor cores, fp32 activations, parity <= 1e-3).
+    $HFG_MODE, else "tf32" (tensor cores, 10-bit-mantissa operands, fp32 accumulate, residual
+    stream of >= 22 mantissa bits, parity <= 1e-3).
     "fp16" keeps tf32's 10-bit mantissa (parity <= 1e-3) at bf16's speed; its
     conversions saturate at +-65504.
     """
