@@ -7,9 +7,10 @@ generator hot path on N B200s (BASELINE.json metric).
     python bench.py --impl reference ...      # the CPU arm: reference path on host cores
 
 Headline line (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE.json configs[1] -- a step is one
-generator forward over 16 utterances x 172 frames (2 s each at 22.05 kHz, hop 256) in tf32 mode (fp32 activations
-in HBM, kind::tf32 MMAs; the on-chip intermediate of a fused ResBlock pair is held as fp16 = tf32's own 10-bit
-mantissa); every rank
+generator forward over 16 utterances x 172 frames (2 s each at 22.05 kHz, hop 256) in tf32 mode: 10-bit-mantissa
+operands, fp32 accumulate, residual stream of >= 22 mantissa bits.  For the default configuration the library
+holds every MMA operand as fp16 (tf32's mantissa, rounded to nearest) and the residual stream as an fp16 pair
+hi + lo ("split plan", hfg_tf32_plan; DESIGN.md section 3), so the MMAs are tcgen05 kind::f16; every rank
 runs its own batch (utterance sharding, no data-path collective): "scaling": "weak".
 
   value  device-timed (CUDA events around each step, L2 flushed between steps, mel already resident in
@@ -453,6 +454,7 @@ def main():
 
         # ---------------- per-kernel profile (separate, untimed pass) ----------------
         h = gen._handle_for(dev)
+        tf32_split = h.tf32_plan_is_split()     # tf32 mode on fp16 operand planes + fp16 hi/lo residual stream
         prof_by_mode = {}
         for m in ([args.mode] if args.no_quality else [args.mode] + [x for x in ("tf32", "fp16", "bf16") if x != args.mode]):
             if m != args.mode and rank != 0:
@@ -535,7 +537,10 @@ def main():
             burst = peaks["bf16_tflops"]
             sustained = peaks["bf16_tflops_sustained"]
             note = "bf16/fp16 dense, burst (a kernel timed alone); MEASURED_PEAKS.json"
-            if mode == "tf32":
+            if mode == "tf32" and tf32_split:
+                note += ("; tf32 mode on the split plan: every MMA of a fused pair is tcgen05 kind::f16 on fp16 operands, "
+                         "so the bf16/fp16 peak applies")
+            if mode == "tf32" and not tf32_split:
                 if tf32_peak:
                     burst, sustained = tf32_peak, tf32_peak * peaks["bf16_tflops_sustained"] / peaks["bf16_tflops"]
                     note = ("tf32 dense burst measured in this run (torch.matmul 8192^3, allow_tf32, best of 10); "
@@ -551,7 +556,7 @@ def main():
                         "achieved": ach, "peak": ffma, "unit": "TFLOP/s", "frac": ach / ffma, "traffic": None,
                         "peak_source": "nominal fp32 FFMA rate 148 SM x 128 lanes x 2 x 1.965 GHz (not a tensor peak)"}
             dom = max(mrf, key=lambda p: p["ms"])
-            if mode == "tf32" and not dom["kernel"].endswith(":conv"):
+            if mode == "tf32" and not tf32_split and not dom["kernel"].endswith(":conv"):
                 # a fused pair in tf32 mode runs conv1 as kind::tf32 and conv2 on the fp16 copy of the on-chip
                 # intermediate (kind::f16): half of its FLOPs at each rate -> the peak of the launch is the
                 # harmonic mean of the two measured peaks
@@ -668,9 +673,13 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": DTYPE[args.mode], "data": "synthetic",
+            "dtype": ("f16 operands (tf32's 10-bit mantissa, round-to-nearest), f32 accumulate, residual stream as an "
+                      "f16 pair hi+lo (22-bit mantissa)") if (args.mode == "tf32" and tf32_split) else DTYPE[args.mode],
+            "data": "synthetic",
             "config": config_dict(world),
             "mode": args.mode,
+            "tf32_plan": ("split: MMAs read fp16 planes (tcgen05 kind::f16), residual stream stored as fp16 hi + lo"
+                          if tf32_split else "fp32 planes, tcgen05 kind::tf32"),
             "timing_notes": {
                 "streams": "timed steps: the 3 resblocks of each MRF on 3 streams (fork/join events); the "
                            "per-kernel roofline pass serialises them so every launch is timed alone",

@@ -218,6 +218,11 @@ int hfg_length_regulate(const float* henc, const int64_t* dur, int32_t batch, in
 /* Number of kernels the last hfg_forward* call on this handle launched. */
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches);
 
+/* How HFG_MODE_TF32 runs on this (committed) handle: *split = 1 when the MMAs read fp16 planes and the residual
+ * stream is stored as an fp16 pair hi + lo (every ResBlock pair fits the fused kernel), 0 when the fp32-plane
+ * tcgen05 kind::tf32 kernels are used.  Both compute 10-bit-mantissa products accumulated in fp32. */
+int hfg_tf32_plan(const hfg_handle* h, int32_t* split);
+
 #ifdef __cplusplus
 }
 #endif

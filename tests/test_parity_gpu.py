@@ -286,6 +286,29 @@ def test_kernel_variants_are_bit_identical(mode):
         assert len(set(hashes)) == 1, list(zip(variants, hashes))
 
 
+def test_tf32_fp32_plane_path_still_matches_the_oracle(record):
+    """HFG_MODE_TF32 runs on fp16 hi + lo planes whenever every ResBlock pair fits the fused kernel (the default
+    configuration and every golden); configurations that do not fit keep the fp32-plane kind::tf32 kernels.  That
+    path is selected here through the tuning library (HFG_TC_TF32_MIXED=0) and checked against the oracle, and
+    the default path must differ from it (else the knob did nothing)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tuning = os.path.join(root, "tts-sambert_hifigan_b200", "lib", "libhfg_b200_tuning.so")
+    res = {}
+    for mixed in ("1", "0"):
+        env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, HFG_LIB_PATH=tuning, HFG_TC_TF32_MIXED=mixed)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), "tf32", "--oracle"],
+                             env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        h = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0].split()[1]
+        e = [l for l in out.stdout.splitlines() if l.startswith("MAXABS")][0].split()
+        res[mixed] = (h, float(e[1]), float(e[2]))
+        print(f"tf32 path mixed={mixed}: max-abs vs oracle {float(e[1]):.3e} (peak {float(e[2]):.3f})")
+    assert res["0"][0] != res["1"][0]
+    record("tf32_fp32_planes_3x97", "tf32", res["0"][1], res["0"][2])
+    assert res["0"][1] <= TOL["tf32"] and res["1"][1] <= TOL["tf32"]
+
+
 def test_debug_prints_match_reference(manifest, capsys):
     gen = pkg.HiFiGANGenerator(debug_shapes=True, mode="fp32").to("cuda:0")
     with torch.no_grad():

@@ -15,3 +15,7 @@ with torch.no_grad():
     wav = gen(mel)
 torch.cuda.synchronize()
 print("HASH", hashlib.sha256(wav.cpu().numpy().tobytes()).hexdigest(), gen.last_launch_count)
+if len(sys.argv) > 2 and sys.argv[2] == "--oracle":        # max-abs error against the oracle on the same input (tests only)
+    import oracle
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in synth.make_weights(cfg, 7).items()}, mel.cpu()).numpy()
+    print("MAXABS", float(abs(wav.cpu().numpy() - ref).max()), float(abs(ref).max()))

@@ -20,6 +20,7 @@ SYMBOLS = [
     "hfg_set_profiling", "hfg_get_profile", "hfg_bench_layer", "hfg_set_mel_layout",
     "hfg_durations_from_log", "hfg_length_regulate_frames", "hfg_length_regulate",
     "hfg_forward_lengths", "hfg_receptive_radius", "hfg_forward_host_submit", "hfg_forward_host_wait",
+    "hfg_tf32_plan",
 ]
 # include/hfg_mel.h (on-device log-mel / log-mel L1)
 MEL_SYMBOLS = ["hfg_mel_create", "hfg_mel_destroy", "hfg_mel_last_error", "hfg_mel_frames", "hfg_log_mel", "hfg_log_mel_l1"]
@@ -99,6 +100,8 @@ def load():
     lib.hfg_forward_host_ex.argtypes = [vp, vp, i32, i32, vp, i32, ctypes.c_uint32]
     lib.hfg_last_launch_count.restype = ctypes.c_int
     lib.hfg_last_launch_count.argtypes = [vp, i64p]
+    lib.hfg_tf32_plan.restype = ctypes.c_int
+    lib.hfg_tf32_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
     lib.hfg_set_profiling.restype = ctypes.c_int
     lib.hfg_set_profiling.argtypes = [vp, i32]
     lib.hfg_get_profile.restype = ctypes.c_int
@@ -285,3 +288,9 @@ class Handle:
         out = ctypes.c_int64()
         self._check(self._lib.hfg_last_launch_count(self._h, ctypes.byref(out)))
         return out.value
+
+    def tf32_plan_is_split(self) -> bool:
+        """True when HFG_MODE_TF32 runs on fp16 operand planes with an fp16 hi + lo residual stream (hfg_tf32_plan)."""
+        out = ctypes.c_int32()
+        self._check(self._lib.hfg_tf32_plan(self._h, ctypes.byref(out)))
+        return bool(out.value)

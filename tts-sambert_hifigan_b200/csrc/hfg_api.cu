@@ -755,6 +755,8 @@ int hfg_bench_layer(hfg_handle* h, int32_t stage, int32_t resblock, int32_t pair
         throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: bad argument");
     if (mode == HFG_MODE_BF16) *ms = tc_bench_layer_impl<PREC_BF16>(h, stage, resblock, pair, which, batch, rows, iters);
     else if (mode == HFG_MODE_FP16) *ms = tc_bench_layer_impl<PREC_FP16>(h, stage, resblock, pair, which, batch, rows, iters);
+    else if (mode == HFG_MODE_TF32 && tc_tf32_mixed(h) && which == 2)
+        *ms = tc_bench_layer_impl<PREC_FP16, true>(h, stage, resblock, pair, which, batch, rows, iters);
     else if (mode == HFG_MODE_TF32) *ms = tc_bench_layer_impl<PREC_TF32>(h, stage, resblock, pair, which, batch, rows, iters);
     else throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: tensor-core modes only");
     HFG_CATCH(h)
@@ -815,6 +817,15 @@ int hfg_length_regulate(const float* henc, const int64_t* dur, int32_t batch, in
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(cum, st);
     return e == cudaSuccess ? HFG_OK : lr_fail(e);
+}
+
+int hfg_tf32_plan(const hfg_handle* hc, int32_t* split) {
+    hfg_handle* h = const_cast<hfg_handle*>(hc);
+    if (!h || !split) return HFG_ERR_INVALID;
+    HFG_TRY(h)
+    if (!h->committed) throw StatusError(HFG_ERR_STATE, "weights not committed");
+    *split = (tc_supported(h) && tc_tf32_mixed(h)) ? 1 : 0;
+    HFG_CATCH(h)
 }
 
 int hfg_last_launch_count(const hfg_handle* h, int64_t* launches) {

@@ -318,6 +318,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -413,17 +418,45 @@ __device__ __forceinline__ void load_cells16(const uint8_t* p, long long plane_s
 // fp32 value as an fp16 pair: hi = fp16(v), lo = fp16(v - hi).  hi + lo carries 22 bits of mantissa (absolute floor
 // 3e-8 in fp16's subnormal range); hi alone is the round-to-nearest 10-bit-mantissa operand a tf32 MMA would see.
 // Both conversions saturate, so the pair stays finite whatever v is.
+// The fp16 halves enter the fp32 adds directly (add / sub.rn.f32.f16 -> one FHADD each, exact), which saves the
+// two conversions per pair a plain unpack would cost -- these epilogues are bound by their instruction count.
 __device__ __forceinline__ void split16(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         h[i] = pack_fp16(v[2 * i], v[2 * i + 1]);
-        float h0, h1;
-        unpack_fp16(h[i], h0, h1);
-        l[i] = pack_fp16(v[2 * i] - h0, v[2 * i + 1] - h1);
+        float d0, d1;                                  // hi - v (exact in fp32); lo = fp16(-(hi - v))
+        asm("{\n\t.reg .b16 h0, h1;\n\tmov.b32 {h0, h1}, %2;\n\t"
+            "sub.rn.f32.f16 %0, h0, %3;\n\tsub.rn.f32.f16 %1, h1, %4;\n\t}"
+            : "=f"(d0), "=f"(d1) : "r"(h[i]), "f"(v[2 * i]), "f"(v[2 * i + 1]));
+        l[i] = pack_fp16(-d0, -d1);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// hi + lo of one cell (8 channels) as fp32
+__device__ __forceinline__ void join16(const uint4& hi, const uint4& lo, float* v) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float l0, l1;
+        unpack_fp16(l[i], l0, l1);
+        asm("{\n\t.reg .b16 h0, h1;\n\tmov.b32 {h0, h1}, %2;\n\t"
+            "add.rn.f32.f16 %0, h0, %3;\n\tadd.rn.f32.f16 %1, h1, %4;\n\t}"
+            : "=f"(v[2 * i]), "=f"(v[2 * i + 1]) : "r"(h[i]), "f"(l0), "f"(l1));
+    }
+}
+// 16 consecutive channels of one row from two cells of the hi planes and two of the lo planes
+__device__ __forceinline__ void load_split16(const uint8_t* hi_p, long long hi_stride, const uint8_t* lo_p, long long lo_stride,
+                                             float (&v)[16]) {
+    uint4 h[2], l[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        h[g] = *reinterpret_cast<const uint4*>(hi_p + g * hi_stride);
+        l[g] = *reinterpret_cast<const uint4*>(lo_p + g * lo_stride);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) join16(h[g], l[g], v + g * 8);
 }
 // 16 consecutive channels of one row -> two cells of the hi planes and two of the lo planes
 __device__ __forceinline__ void store_split16(uint8_t* hi_p, uint8_t* lo_p, long long plane_stride, const float (&v)[16]) {
@@ -434,6 +467,17 @@ __device__ __forceinline__ void store_split16(uint8_t* hi_p, uint8_t* lo_p, long
         *reinterpret_cast<uint4*>(hi_p + g * plane_stride) = hi;
         *reinterpret_cast<uint4*>(lo_p + g * plane_stride) = lo;
     }
+}
+// two 16-byte cells of consecutive rows of one chunk plane (32-byte aligned): one 256-bit store (STG.256)
+__device__ __forceinline__ void st_global_256(uint8_t* p, const uint4& a, const uint4& b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+// the same cell of two consecutive rows: one 32-byte store when both rows are valid (p = row 0, 32-byte aligned)
+__device__ __forceinline__ void store_cell_rows2(uint8_t* p, const uint4& c0, const uint4& c1, bool v0, bool v1) {
+    if (v0 && v1) st_global_256(p, c0, c1);
+    else if (v0) *reinterpret_cast<uint4*>(p) = c0;
+    else if (v1) *reinterpret_cast<uint4*>(p + 16) = c1;
 }
 __device__ __forceinline__ void load_f32x16(const uint8_t* p, long long plane_stride, float (&v)[16]) {
     float4 u[4];

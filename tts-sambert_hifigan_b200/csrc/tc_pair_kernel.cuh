@@ -467,13 +467,12 @@ tc_pair_kernel(const TcPairArgs a) {
                         // whose tile-i values it has itself already read in epi2
                         if (split2 && (((pp * N + col) >> 5) & 1) != half) continue;
                         float v[16];
-                        load_cells16<P>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
+                        if constexpr (LO)
+                            load_split16(rp + (long long)(c16 / CW) * a_plane, a_plane,
+                                         lp + (long long)(c16 / CW) * ((long long)RL * 16), (long long)RL * 16, v);
+                        else
+                            load_cells16<P>(rp + (long long)(c16 / CW) * a_plane, a_plane, v);
                         float prev[16];
-                        if constexpr (LO) {
-                            load_cells16<P>(lp + (long long)(c16 / CW) * ((long long)RL * 16), (long long)RL * 16, prev);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] += prev[i];
-                        }
                         if (add_prev && a.n_sum == 0) load_f32x16(accp + (long long)(col / 4) * a.acc_pstride, a.acc_pstride, prev);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = lrelu_inv(v[i], inv_slope);
@@ -551,7 +550,56 @@ tc_pair_kernel(const TcPairArgs a) {
             mbar_wait_sleep(ACC2_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(9, it);
-            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8); mt += mt2_step) {
+            // space-to-depth form with both time steps of a GEMM row in this thread: rows 2m and 2m + 1 of a chunk plane
+            // are adjacent, so every cell pair leaves as ONE 32-byte store (lanes 32 bytes apart: full sectors) instead
+            // of two 16-byte stores with a 32-byte lane stride
+            // (compiled only into the single-CTA 2-byte variants, the ones the space-to-depth rule selects: the CTA-pair
+            // and tf32 variants run at their register cap and would pay for the extra path with spills)
+            const bool rows2 = CTAS == 1 && P != PREC_TF32 && a.s2d && !split2 && !acc_store_mode;
+            if constexpr (CTAS == 1 && P != PREC_TF32)
+            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8) && rows2; mt += mt2_step) {
+                const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
+                const int lr = (mt * 128 + row) * 2;
+                const int t = t0 + lr;
+                const bool v0 = real && lr < a.TO && t < a.T, v1 = real && lr + 1 < a.TO && t + 1 < a.T;
+                const long long row_bytes = (long long)(kPadL + t) * 16;
+                uint8_t* op = a.out + (long long)b * a.o_bstride + row_bytes;
+                for (int cb = 0; cb < N; cb += 8) {          // 8 channels of both rows at a time (register budget of the MINB = 2 variants)
+                    uint32_t r0[8], r1[8];
+                    tmem_ld8(tbase + (uint32_t)cb, r0);
+                    tmem_ld8(tbase + (uint32_t)(N + cb), r1);
+                    tmem_ld_wait();
+                    if (!v0 && !v1) continue;
+                    float x0[8], x1[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { x0[i] = __uint_as_float(r0[i]); x1[i] = __uint_as_float(r1[i]); }
+                    if (a.acc_mode == TC_ACC_FINAL) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { x0[i] *= inv_div; x1[i] *= inv_div; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { x0[i] = lrelu(x0[i], slope); x1[i] = lrelu(x1[i], slope); }
+                    if (LO && a.out32) {
+                        uint8_t* p32 = a.out32 + (long long)b * a.o32_bstride + row_bytes + (long long)(cb / 4) * a.o32_pstride;
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            store_cell_rows2(p32 + g * a.o32_pstride, floats_to_cell<PREC_TF32>(x0 + 4 * g),
+                                             floats_to_cell<PREC_TF32>(x1 + 4 * g), v0, v1);
+                    } else if (LO && a.out_lo) {
+                        uint4 h0, l0, h1, l1;
+                        split16(x0, h0, l0);
+                        split16(x1, h1, l1);
+                        store_cell_rows2(op + (long long)(cb / CW) * a.o_pstride, h0, h1, v0, v1);
+                        store_cell_rows2(a.out_lo + (long long)b * a.o_bstride + row_bytes + (long long)(cb / CW) * a.o_pstride, l0, l1, v0, v1);
+                    } else {
+                        uint8_t* ph = op + (long long)(cb / CW) * a.o_pstride;
+#pragma unroll
+                        for (int g = 0; g < 8 / CW; ++g)
+                            store_cell_rows2(ph + g * a.o_pstride, floats_to_cell<P>(x0 + CW * g), floats_to_cell<P>(x1 + CW * g), v0, v1);
+                    }
+                }
+            }
+            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8) && !rows2; mt += mt2_step) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
                 for (int c0 = 32 * ch2; c0 < N2; c0 += 32 * cs2) {
                     const int pp = c0 >= N ? 1 : 0, cb = c0 - pp * N;   // time step of this GEMM row, channel base (N % 32 == 0 when PP = 2)

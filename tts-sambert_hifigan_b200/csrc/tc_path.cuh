@@ -1008,13 +1008,16 @@ static void tc_forward_impl(hfg_handle* h, const float* mel, int B, int T, float
 
 // Micro-benchmark of ONE MRF convolution launch on scratch planes (tuning / ncu).
 // which: 0 = convs1[pair], 1 = convs2[pair] (with residual).  Returns avg ms per launch.
-template <int P>
+// LO (which = 2 only): the hi + lo variant of the fused pair (split plan of the tf32 mode), on fp16 planes
+template <int P, bool LO = false>
 static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pair, int which, int B, int T, int iters) {
     const PairLayers& PL = h->mrfs.at(stage).at(resblock).at(pair);
     const ConvLayer& L = which == 1 ? PL.c2 : PL.c1;
     size_t cur = 0;
     const int cw = Prec<P>::CW;
     TcPlane in = tc_plane(B, L.cin, T, cw, cur), out = tc_plane(B, L.cout, T, cw, cur), res = tc_plane(B, L.cout, T, cw, cur);
+    TcPlane in_lo = tc_plane(B, L.cin, T, cw, cur);        // LO: lo twin of `in`; `res` serves as the lo twin of `out`
+    if (LO && which != 2) throw StatusError(HFG_ERR_INVALID, "hfg_bench_layer: the tf32 split plan only has fused pairs");
     char* ws = nullptr;
     check_cuda(cudaMalloc((void**)&ws, cur), "cudaMalloc(bench)");
     check_cuda(cudaMemset(ws, 0, cur), "cudaMemset(bench)");
@@ -1038,9 +1041,10 @@ static float tc_bench_layer_impl(hfg_handle* h, int stage, int resblock, int pai
     if (which == 2 && !g.ok) throw StatusError(HFG_ERR_UNSUPPORTED, "fused pair does not fit for this layer");
     auto launch = [&]() {
         if (which == 2)
-            tc_launch_pair<P>(h, st, PL, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
-                              (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
-                              nullptr, 0, nullptr, B, T, "bench");
+            tc_launch_pair<P, LO>(h, st, PL, g, (uint8_t*)ws + in.off, in.bstride, in.pstride, in.nchunks,
+                                  (uint8_t*)ws + out.off, out.bstride, out.pstride, nullptr, 0, 0, TC_ACC_NONE, 1.f,
+                                  nullptr, 0, nullptr, B, T, "bench",
+                                  LO ? (uint8_t*)ws + in_lo.off : nullptr, LO ? (uint8_t*)ws + res.off : nullptr);
         else
             tc_launch_conv<P>(h, st, a, B, L.cout, "bench", 0, 0);
     };
