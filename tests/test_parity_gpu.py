@@ -268,7 +268,9 @@ def test_kernel_variants_are_bit_identical(mode):
                dict(T), dict(T, HFG_TC_UP_PERSIST="0"), dict(T, HFG_TC_UP_PERSIST="0", HFG_TC_UPS_STACK="0"),
                dict(T, HFG_TC_UPS_STACK="1"), dict(T, HFG_TC_UP_RESBLOCK="1", HFG_TC_UP_WIDE="1"),
                dict(T, HFG_TC_STREAMS="1"), dict(T, HFG_TC_PAIR_CTAS="1"),
-               dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0")]
+               dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0"),
+               dict(T, HFG_TC_PAIR_GROUPS="2"),                 # every tile as two independently pipelined halves
+               dict(T, HFG_TC_UP_CONTIG="1")]                   # contiguous item blocks in the persistent conv kernel
     group_b = [dict(T, HFG_TC_S2D="0"), dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1"),
                dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_PAIR_MT="1")]
     # group C: the space-to-depth form forced onto every layer that can take it (C = 64 too, all k)

@@ -71,6 +71,15 @@ struct TcPairArgs {
     // A-operand read (the 64 B/clk shared-memory read that bounds the narrow layers) then feeds twice the output
     // columns: conv2 needs (k + 1) / 2 * 2 MMAs per 256 time steps instead of 2 * k.  s2d = 0: k2 = k, tap_group2 = tap_group.
     int s2d, k2, tap_group2;
+    // groups = 2: the tile runs as TWO INDEPENDENT HALVES (sub-tiles [0, MT/2) and [MT/2, MT)), each with its own
+    // accumulator / H-tile barriers and its own four epilogue warps.  The MMA warp runs conv1 of the upper half, conv1
+    // of the lower half, conv2 of the upper half (it needs no H row of the lower one), conv2 of the lower half; so one
+    // half's epi1 overlaps the other half's conv1, and its epi2 + the next tile's pre2 overlap the other half's
+    // conv2 -- the k = 3 / 7 layers, whose tile time is the serial chain pre2 -> epi1 -> conv2 -> epi2 of ALL eight
+    // warps, lose most of the time the epilogue warps spent waiting for whole-tile accumulators.  Costs: the
+    // weight stages of each convolution are streamed once per half, and every activation K block of the tile must
+    // be resident at once (sa == number of K blocks).  groups = 1: one accumulator set per tile, as before.
+    int groups;
     unsigned w_stage_bytes;   // bytes of one W ring slot (the larger of the conv1 / conv2 stage)
     int kbc;          // 16-byte cells per K block
     int poll_ns;      // producer back-off when both rings are full
@@ -158,7 +167,12 @@ tc_pair_kernel(const TcPairArgs a) {
     auto W_EMPTY = [&](int i) { return bar0 + 8u * (2 * kPairMaxSA + kMaxSW + i); };
     const uint32_t ACC1_FULL = bar0 + 8u * (2 * kPairMaxSA + 2 * kMaxSW);
     const uint32_t H_READY = ACC1_FULL + 8, ACC2_FULL = ACC1_FULL + 16, LO_FULL = ACC1_FULL + 24;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairMaxSA + 2 * kMaxSW + 4);
+    // second set for the upper half of a tile run as two halves (a.groups == 2); the lower half -- the one whose
+    // conv2 completes last -- uses the first set
+    const uint32_t ACC1_FULL_B = ACC1_FULL + 32, H_READY_B = ACC1_FULL + 40, ACC2_FULL_B = ACC1_FULL + 48;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPairMaxSA + 2 * kMaxSW + 7);
+    const int GR = a.groups;
+    const int MTg = MT / GR, MT2g = MT2 / GR;         // sub-tiles per half
 
     uint32_t ncols = 32;
     while ((int)ncols < 2 * MT * N) ncols <<= 1;
@@ -170,9 +184,12 @@ tc_pair_kernel(const TcPairArgs a) {
         for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), full_count); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
         for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), full_count); mbar_init(W_EMPTY(i), 1); }
         mbar_init(ACC1_FULL, 1);
-        mbar_init(H_READY, kPairEpiWarps * CTAS);
+        mbar_init(H_READY, (kPairEpiWarps / GR) * CTAS);
         mbar_init(ACC2_FULL, 1);
         mbar_init(LO_FULL, 1);
+        mbar_init(ACC1_FULL_B, 1);
+        mbar_init(H_READY_B, (kPairEpiWarps / GR) * CTAS);
+        mbar_init(ACC2_FULL_B, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -239,7 +256,7 @@ tc_pair_kernel(const TcPairArgs a) {
         // profiles/r1_tuning.md section 6.)
         const int groups = (k + G - 1) / G, groups2 = (k2 + G2 - 1) / G2;
         int a_sc = next_live(sched0), a_kb = 0;                  // next A block: schedule slot, K block
-        int w_sc = a_sc, w_conv = 0, w_kb = 0, w_g = 0;          // next W stage
+        int w_sc = a_sc, w_conv = 0, w_kb = 0, w_g = 0, w_pass = 0;   // next W stage (each convolution's stages once per half)
         int a_t = 0, w_t = 0;                                    // ordinals of those slots among this CTA's live ones
         int l_sc = LO ? a_sc : n_sched, l_t = 0;                 // LO kernels: next tile whose lo rows go into the H-tile buffer
         uint32_t idle = 0;
@@ -300,7 +317,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 }
                 __syncwarp();
                 if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
-                if (++w_g == w_groups) { w_g = 0; if (++w_kb == w_nkb) { w_kb = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } }
+                if (++w_g == w_groups) { w_g = 0; if (++w_kb == w_nkb) { w_kb = 0; if (++w_pass == GR) { w_pass = 0; if (++w_conv == 2) { w_conv = 0; ++w_t; w_sc = next_live(w_sc + sched_step); } } } }
                 did = true;
             }
             if (did) { idle = 0; t_idle0 = 0; continue; }
@@ -324,7 +341,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // slot, so slots are forwarded independently instead of through one serial wait chain ----
             int n_my = 0;
             for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step)) ++n_my;
-            const int stages_per_tile = n_kb * ((k + G - 1) / G) + n_kb2 * ((k2 + G2 - 1) / G2);
+            const int stages_per_tile = GR * (n_kb * ((k + G - 1) / G) + n_kb2 * ((k2 + G2 - 1) / G2));
             const int total_w = n_my * stages_per_tile, total_a = n_my * n_kb;
             if (lane < a.sw) {
                 const int uses = total_w / a.sw + (lane < total_w % a.sw ? 1 : 0);
@@ -346,71 +363,83 @@ tc_pair_kernel(const TcPairArgs a) {
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t it = 0;
         for (int sc = next_live(sched0); sc < n_sched; sc = next_live(sc + sched_step), ++it) {
-            // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1 ----
-            uint32_t acc_on = 0;
-            for (int kb = 0; kb < n_kb; ++kb) {
-                const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
-                const int ksteps = nck >> 1;
-                mbar_wait(A_FULL(sa_i), sa_ph);
-                tc_fence_after();
-                if (kb == 0) HFG_TL(1, it);
-                const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
-                for (int tap0 = 0; tap0 < k; tap0 += G) {
-                    const int g = (k - tap0) < G ? (k - tap0) : G;
-                    mbar_wait(W_FULL(sw_i), sw_ph);
-                    tc_fence_after();
-                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
-                    if (leader) {
-                        for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
-                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
-                            const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : a.dil));
-                            for (int mt = 0; mt < MT; ++mt)
-                                umma_ksteps<P, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                        2u * (uint32_t)R1, 2u * (uint32_t)NB, idesc, ksteps,
-                                                        acc_on | (uint32_t)tt);
-                        }
-                        commit(W_EMPTY(sw_i));
+            // ---- conv1: acc1 = sum_{kb,tap} A(+tap*d rows) * W1, one pass per half (upper half first) ----
+            const int sa_i0 = sa_i, sa_ph0 = sa_ph;
+            for (int gp = 0; gp < GR; ++gp) {
+                const int grp = GR - 1 - gp;
+                sa_i = sa_i0; sa_ph = sa_ph0;                  // every pass walks the tile's activation stages
+                uint32_t acc_on = 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    const int nck = (n_chunks - KBC * kb) < KBC ? (n_chunks - KBC * kb) : KBC;
+                    const int ksteps = nck >> 1;
+                    if (gp == 0) {                             // (still resident in the later pass)
+                        mbar_wait(A_FULL(sa_i), sa_ph);
+                        tc_fence_after();
                     }
+                    if (kb == 0 && gp == 0) HFG_TL(1, it);
+                    const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa_i * a_stage_bytes) & 0x3FFFFu) >> 4) | a_lbo;
+                    for (int tap0 = 0; tap0 < k; tap0 += G) {
+                        const int g = (k - tap0) < G ? (k - tap0) : G;
+                        mbar_wait(W_FULL(sw_i), sw_ph);
+                        tc_fence_after();
+                        const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b_lbo;
+                        if (leader) {
+                            for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
+                                const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB);
+                                const uint32_t a_lo1 = a_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : a.dil));
+                                for (int mt = grp * MTg; mt < (grp + 1) * MTg; ++mt)
+                                    umma_ksteps<P, CTAS>(acc1 + (uint32_t)(mt * N), d_hi, a_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                            2u * (uint32_t)R1, 2u * (uint32_t)NB, idesc, ksteps,
+                                                            acc_on | (uint32_t)tt);
+                            }
+                            commit(W_EMPTY(sw_i));
+                        }
+                        __syncwarp();
+                        acc_on = 1;
+                        if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                    }
+                    if (leader && gp == GR - 1) commit(A_EMPTY(sa_i));
                     __syncwarp();
-                    acc_on = 1;
-                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
+                    if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
                 }
-                if (leader) commit(A_EMPTY(sa_i));
+                if (leader) commit(grp ? ACC1_FULL_B : ACC1_FULL);
                 __syncwarp();
-                if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
             }
-            if (leader) commit(ACC1_FULL);
-            __syncwarp();
             HFG_TL(2, it);
-            // ---- conv2: acc2 (pre-loaded with x + b2) += sum_{kb,tap} H(+tap rows) * W2 ----
-            if constexpr (CTAS == 2) mbar_wait_cluster(H_READY, it & 1); else mbar_wait(H_READY, it & 1);
-            tc_fence_after();
-            HFG_TL(3, it);
-            for (int kb = 0; kb < n_kb2; ++kb) {
-                const int nck = (n_chunks2 - KBC * kb) < KBC ? (n_chunks2 - KBC * kb) : KBC;
-                const int ksteps = nck >> 1;
-                const uint32_t h_lo0 = h_lo_base + (uint32_t)(KBC * kb * RH);
-                for (int tap0 = 0; tap0 < k2; tap0 += G2) {
-                    const int g = (k2 - tap0) < G2 ? (k2 - tap0) : G2;
-                    mbar_wait(W_FULL(sw_i), sw_ph);
-                    tc_fence_after();
-                    const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b2_lbo;
-                    if (leader) {
-                        for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
-                            const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB2);
-                            const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : 1));
-                            for (int mt = 0; mt < MT2; ++mt)
-                                umma_ksteps<P2, CTAS>(acc2 + (uint32_t)(mt * N2), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
-                                                        2u * (uint32_t)RH, 2u * (uint32_t)NB2, idesc2, ksteps, 1u);
+            // ---- conv2: acc2 (pre-loaded with x + b2) += sum_{kb,tap} H(+tap rows) * W2; the upper half reads H rows of
+            // its own half only, the lower half also the first 2 p2 rows of the upper one (complete by then) ----
+            for (int gp = 0; gp < GR; ++gp) {
+                const int grp = GR - 1 - gp;
+                const uint32_t h_ready = grp ? H_READY_B : H_READY;
+                if constexpr (CTAS == 2) mbar_wait_cluster(h_ready, it & 1); else mbar_wait(h_ready, it & 1);
+                tc_fence_after();
+                if (gp == 0) HFG_TL(3, it);
+                for (int kb = 0; kb < n_kb2; ++kb) {
+                    const int nck = (n_chunks2 - KBC * kb) < KBC ? (n_chunks2 - KBC * kb) : KBC;
+                    const int ksteps = nck >> 1;
+                    const uint32_t h_lo0 = h_lo_base + (uint32_t)(KBC * kb * RH);
+                    for (int tap0 = 0; tap0 < k2; tap0 += G2) {
+                        const int g = (k2 - tap0) < G2 ? (k2 - tap0) : G2;
+                        mbar_wait(W_FULL(sw_i), sw_ph);
+                        tc_fence_after();
+                        const uint32_t b_stage = ((smem_u32(sW + (size_t)sw_i * w_stage_bytes) & 0x3FFFFu) >> 4) | b2_lbo;
+                        if (leader) {
+                            for (int tt = 0; tt < g && !HFG_DBG(a, 16); ++tt) {
+                                const uint32_t b_lo = b_stage + (uint32_t)(tt * nck * NB2);
+                                const uint32_t h_lo1 = h_lo0 + (uint32_t)((tap0 + tt) * (HFG_DBG(a, 4) ? 8 : 1));
+                                for (int mt = grp * MT2g; mt < (grp + 1) * MT2g; ++mt)
+                                    umma_ksteps<P2, CTAS>(acc2 + (uint32_t)(mt * N2), d_hi, h_lo1 + (uint32_t)(mt * 128), b_lo,
+                                                            2u * (uint32_t)RH, 2u * (uint32_t)NB2, idesc2, ksteps, 1u);
+                            }
+                            commit(W_EMPTY(sw_i));
                         }
-                        commit(W_EMPTY(sw_i));
+                        __syncwarp();
+                        if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                     }
-                    __syncwarp();
-                    if (++sw_i == a.sw) { sw_i = 0; sw_ph ^= 1; }
                 }
+                if (leader) commit(grp ? ACC2_FULL_B : ACC2_FULL);
+                __syncwarp();
             }
-            if (leader) commit(ACC2_FULL);
-            __syncwarp();
             HFG_TL(4, it);
         }
         }   // leader / single-CTA issue path
@@ -422,11 +451,17 @@ tc_pair_kernel(const TcPairArgs a) {
         // ... or, with a single sub-tile, alternate 32-column steps.  acc1 has MT sub-tiles of N columns, acc2 has
         // MT2 sub-tiles of N2 columns (MT / 2 and 2 N in space-to-depth form): each accumulator has its own split,
         // and every phase that touches acc2 (pre2, epi2) uses the same one
-        const bool split1 = MT == 1, split2 = MT2 == 1;
-        const int mt_first = split1 ? 0 : half, mt_step = split1 ? 1 : 2;
+        // With the tile run as two halves (GR == 2) the warps of `half` own ALL sub-tiles and columns of that half.
+        const bool split1 = GR == 1 && MT == 1, split2 = GR == 1 && MT2 == 1;
+        const int mt_first = GR == 2 ? half * MTg : (split1 ? 0 : half), mt_end = GR == 2 ? (half + 1) * MTg : MT;
+        const int mt_step = (GR == 2 || split1) ? 1 : 2;
         const int cs = split1 ? 2 : 1, ch = split1 ? half : 0;           // acc1: 32-column-step stride / phase
-        const int mt2_first = split2 ? 0 : half, mt2_step = split2 ? 1 : 2;
+        const int mt2_first = GR == 2 ? half * MT2g : (split2 ? 0 : half), mt2_end = GR == 2 ? (half + 1) * MT2g : MT2;
+        const int mt2_step = (GR == 2 || split2) ? 1 : 2;
         const int cs2 = split2 ? 2 : 1, ch2 = split2 ? half : 0;         // acc2
+        const bool upper = GR == 2 && half == 1;                         // this warp's half uses the second barrier set
+        const uint32_t acc1_full = upper ? ACC1_FULL_B : ACC1_FULL, h_ready = upper ? H_READY_B : H_READY;
+        const uint32_t acc2_full = upper ? ACC2_FULL_B : ACC2_FULL;
         const int row = quarter * 32 + lane;          // row inside a 128-row sub-tile
         const uint32_t lane_sel = (uint32_t)(quarter * 32) << 16;
         const float slope = a.slope, inv_slope = 1.0f / a.slope;
@@ -448,7 +483,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 mbar_wait_sleep(A_FULL(sa_i), sa_ph, (uint32_t)a.epi_sleep_ns);
                 if (kb == 0 && e == 0) HFG_TL(5, it);
                 const uint8_t* sa_p = sA + (size_t)sa_i * a_stage_bytes;
-                for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8); mt += mt2_step) {
+                for (int mt = mt2_first; mt < mt2_end && !HFG_DBG(a, 8); mt += mt2_step) {
                   for (int pp = 0; pp < PP; ++pp) {                     // the time steps of this GEMM row
                     const int lr = (mt * 128 + row) * PP + pp;          // output row inside the tile
                     const int t = t0 + lr;
@@ -502,12 +537,12 @@ tc_pair_kernel(const TcPairArgs a) {
             if constexpr (LO) asm volatile("bar.sync 1, %0;" ::"n"(32 * kPairEpiWarps) : "memory");
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
             if (e == 0) HFG_TL(6, it);
-            mbar_wait_sleep(ACC1_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
+            mbar_wait_sleep(acc1_full, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(7, it);
             // only tiles that touch an utterance edge have H rows outside [0, T) to zero
             const bool edge_tile = (t0 - a.p2 < 0) || (t0 - a.p2 + MT * 128 > a.T);
-            for (int mt = mt_first; mt < MT && !HFG_DBG(a, 8); mt += mt_step) {
+            for (int mt = mt_first; mt < mt_end && !HFG_DBG(a, 8); mt += mt_step) {
                 const int hr = mt * 128 + row;                          // H row inside the tile
                 const int th = t0 - a.p2 + hr;                          // its time step
                 const bool drop = edge_tile && !(th >= 0 && th < a.T);  // conv2 zero-pads ITS input
@@ -542,12 +577,12 @@ tc_pair_kernel(const TcPairArgs a) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CTAS == 2 && rank == 1) mbar_arrive_remote(H_READY, 0);
-                else mbar_arrive(H_READY);
+                if (CTAS == 2 && rank == 1) mbar_arrive_remote(h_ready, 0);
+                else mbar_arrive(h_ready);
             }
             // ---------- epi2: acc2 -> global ----------
             if (e == 0) HFG_TL(8, it);
-            mbar_wait_sleep(ACC2_FULL, it & 1, (uint32_t)a.epi_sleep_ns);
+            mbar_wait_sleep(acc2_full, it & 1, (uint32_t)a.epi_sleep_ns);
             tc_fence_after();
             if (e == 0) HFG_TL(9, it);
             // space-to-depth form with both time steps of a GEMM row in this thread: rows 2m and 2m + 1 of a chunk plane
@@ -557,7 +592,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // and tf32 variants run at their register cap and would pay for the extra path with spills)
             const bool rows2 = CTAS == 1 && P != PREC_TF32 && a.s2d && !split2 && !acc_store_mode;
             if constexpr (CTAS == 1 && P != PREC_TF32)
-            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8) && rows2; mt += mt2_step) {
+            for (int mt = mt2_first; mt < mt2_end && !HFG_DBG(a, 8) && rows2; mt += mt2_step) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
                 const int lr = (mt * 128 + row) * 2;
                 const int t = t0 + lr;
@@ -599,7 +634,7 @@ tc_pair_kernel(const TcPairArgs a) {
                     }
                 }
             }
-            for (int mt = mt2_first; mt < MT2 && !HFG_DBG(a, 8) && !rows2; mt += mt2_step) {
+            for (int mt = mt2_first; mt < mt2_end && !HFG_DBG(a, 8) && !rows2; mt += mt2_step) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
                 for (int c0 = 32 * ch2; c0 < N2; c0 += 32 * cs2) {
                     const int pp = c0 >= N ? 1 : 0, cb = c0 - pp * N;   // time step of this GEMM row, channel base (N % 32 == 0 when PP = 2)

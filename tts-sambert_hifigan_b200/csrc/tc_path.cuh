@@ -233,7 +233,7 @@ static inline int tc_prec_of_mode(int mode) {
 }
 static inline bool tc_is_tc_mode(int mode) { return mode == HFG_MODE_TF32 || mode == HFG_MODE_BF16 || mode == HFG_MODE_FP16; }
 
-struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; int s2d, k2, G2; size_t stage; };
+struct PairGeom { int MT, sa, sw, G, R1, RH, TO, ctas, kbc; size_t smem; int occ; bool ok; int s2d, k2, G2; size_t stage; int groups; };
 static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P, int n_chunks, int prec);
 
 // How the MRF sum (reference models/hifigan.py:126-131) of stage i is formed.
@@ -487,6 +487,10 @@ static bool tc_launch_up(hfg_handle* h, cudaStream_t st, TcConvArgs a, int B, in
     ua.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
     const size_t smem = smem_need(MT, sa, sw);
     const int grid = std::min(ua.n_items, h->sm_count);
+    // items of a CTA: strided (item, item + grid, ...) or one contiguous block -- the phases / channel tiles of one
+    // activation tile are adjacent items, so a block keeps them on one SM back to back (their output cells interleave
+    // in the same sectors, the tile comes from L2 again while it is hot)
+    ua.contig = env_int("HFG_TC_UP_CONTIG", 0) ? (ua.n_items + grid - 1) / grid : 0;
     if (env_int("HFG_TC_VERBOSE", 0))
         fprintf(stderr, "[up] %s N=%d MT=%d G=%d sa=%d sw=%d smem=%zu grid=%d items=%d\n", label, a.N, MT, G, sa, sw, smem,
                 grid, ua.n_items);
@@ -594,6 +598,14 @@ static inline PairGeom tc_pair_geometry(const hfg_handle* h, const PairLayers& P
             c.ctas = ctas; c.kbc = kbc;
             c.MT = MT; c.sa = sa; c.sw = sw; c.G = G; c.R1 = R1; c.RH = RH; c.TO = MT * 128 - 2 * p2;
             c.s2d = s2d ? 1 : 0; c.k2 = k2; c.G2 = G2; c.stage = stage;
+            // the tile as two independent halves (TcPairArgs::groups): where the tile has an even number of sub-tiles
+            // in both accumulators and every activation K block is resident, for the layers whose tile time is the
+            // epilogue chain rather than the MMAs (k <= 7; k = 11 is MMA-bound and would only pay the second weight pass)
+            // Measured (profiles/r2_tuning.md section 13): bit-identical, but slower on every layer except C = 128 k = 3
+            // (50.2 -> 48.8 us): the second weight pass doubles the MMA warp's per-stage barrier round trips.  Off.
+            const int gr_want = env_int("HFG_TC_PAIR_GROUPS", 0);
+            c.groups = (gr_want && MT % 2 == 0 && (!s2d || MT % 4 == 0) && sa == n_kb &&
+                        (gr_want == 2 || k <= env_int("HFG_TC_PAIR_GROUPS_KMAX", 7))) ? 2 : 1;
             c.smem = fixed + (size_t)sw * stage;
             c.occ = std::max(1, std::min((int)((227 * 1024) / (c.smem + 1024)), 512 / ncols));
             c.ok = true;
@@ -641,6 +653,7 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.w_half_stride = L.c1.tc.half_stride[P][vk];
     a.w2_half_stride = g.s2d ? L.c2.tc.s2d_half_stride[P2] : L.c2.tc.half_stride[P2][vk];
     a.s2d = g.s2d; a.k2 = g.k2; a.tap_group2 = g.G2; a.w_stage_bytes = (unsigned)g.stage;
+    a.groups = g.groups;
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
@@ -698,8 +711,8 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
                              : (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
                                (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     if (env_int("HFG_TC_VERBOSE", 0))
-        fprintf(stderr, "[pair] lo=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
-                (int)LO, a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
+        fprintf(stderr, "[pair] gr=%d lo=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
+                g.groups, (int)LO, a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
     h->prof_begin(st, label, flops, bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

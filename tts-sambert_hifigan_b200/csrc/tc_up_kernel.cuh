@@ -24,6 +24,7 @@ struct TcUpArgs {
     int n_ctile;         // channel tiles per phase
     int cout_total;      // bias entries staged in shared memory (virtual channels when phases are stacked)
     int epi_sleep_ns;    // epilogue warps: longest sleep between polls of the accumulator barrier (0 = spin)
+    int contig;          // > 0: CTA c runs the contiguous items [c * contig, (c + 1) * contig); 0: items c, c + grid, ...
 };
 
 template <int P>
@@ -80,7 +81,8 @@ tc_up_kernel(const TcUpArgs ua) {
     const uint32_t tmem_base = *tmem_slot;
 
     // work items of this CTA: item, item + gridDim.x, ...
-    const int item0 = (int)blockIdx.x, item_step = (int)gridDim.x;
+    const int item0 = ua.contig ? (int)blockIdx.x * ua.contig : (int)blockIdx.x, item_step = ua.contig ? 1 : (int)gridDim.x;
+    const int item_end = ua.contig ? (item0 + ua.contig < ua.n_items ? item0 + ua.contig : ua.n_items) : ua.n_items;
     auto taps_of = [&](int phase) { return a.phases > 1 ? (a.k - phase + a.u - 1) / a.u : a.taps_max; };
     // variable-length batches (a.len_rows: OUTPUT rows utterance b needs, or null): an item whose tile starts at
     // or beyond the last q position that utterance needs is skipped by every role alike
@@ -90,7 +92,7 @@ tc_up_kernel(const TcUpArgs ua) {
         const int q0 = (tile % a.tiles_per_batch) * MT * 128;
         return q0 < tc_len_nq(a, a.len_rows[tile / a.tiles_per_batch]);
     };
-    auto next_live = [&](int item) { while (item < ua.n_items && !item_live(item)) item += item_step; return item; };
+    auto next_live = [&](int item) { while (item < item_end && !item_live(item)) item += item_step; return item; };
 
     if (warp == 0) {
         // ===================== producer: two independent streams (activation K blocks, weight stages) =====================
@@ -100,9 +102,9 @@ tc_up_kernel(const TcUpArgs ua) {
         int w_item = a_item, w_kb = 0, w_tap0 = 0;          // next weight stage
         uint32_t idle = 0;
         long long t_idle0 = 0;
-        while (a_item < ua.n_items || w_item < ua.n_items) {
+        while (a_item < item_end || w_item < item_end) {
             bool did = false;
-            if (a_item < ua.n_items && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
+            if (a_item < item_end && mbar_test(A_EMPTY(sa_i), sa_ph ^ 1)) {
                 const int tile = a_item / ua.pn_per_tile;
                 const int b = tile / a.tiles_per_batch;
                 const int q0 = (tile % a.tiles_per_batch) * MT * 128;
@@ -120,7 +122,7 @@ tc_up_kernel(const TcUpArgs ua) {
                 if (++a_kb == n_kb) { a_kb = 0; a_item = next_live(a_item + item_step); }
                 did = true;
             }
-            if (w_item < ua.n_items && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
+            if (w_item < item_end && mbar_test(W_EMPTY(sw_i), sw_ph ^ 1)) {
                 const int pn = w_item % ua.pn_per_tile;
                 const int phase = pn / ua.n_ctile, ntile = pn % ua.n_ctile;
                 const int taps = taps_of(phase);
@@ -155,7 +157,7 @@ tc_up_kernel(const TcUpArgs ua) {
         const uint32_t a_lbo = ((uint32_t)R) << 16, b_lbo = ((uint32_t)N) << 16;
         int sa_i = 0, sa_ph = 0, sw_i = 0, sw_ph = 0;
         uint32_t it = 0;
-        for (int item = next_live(item0); item < ua.n_items; item = next_live(item + item_step), ++it) {
+        for (int item = next_live(item0); item < item_end; item = next_live(item + item_step), ++it) {
             const int pn = item % ua.pn_per_tile;
             const int taps = taps_of(pn / ua.n_ctile);
             const uint32_t buf = it & 1u;
@@ -207,7 +209,7 @@ tc_up_kernel(const TcUpArgs ua) {
         const bool acc_store = a.acc_mode == TC_ACC_WRITE || a.acc_mode == TC_ACC_ADD;
         const int col_step = 32 * (n_epi_warps / 4);
         uint32_t it = 0;
-        for (int item = next_live(item0); item < ua.n_items; item = next_live(item + item_step), ++it) {
+        for (int item = next_live(item0); item < item_end; item = next_live(item + item_step), ++it) {
             const int tile = item / ua.pn_per_tile, pn = item % ua.pn_per_tile;
             const int phase = pn / ua.n_ctile, ntile = pn % ua.n_ctile;
             const int b = tile / a.tiles_per_batch;
