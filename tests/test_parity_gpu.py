@@ -5,7 +5,8 @@ Tolerances (max-abs on the waveform, whose peak is 0.03-0.07 at random init) are
 largest value measured on B200 over all cases of this file (profiles/r2_parity.md lists the
 measured numbers, written by the `record` fixture into gpurun_out/parity_r2.jsonl):
   fp32  5e-7   fp32 FFMA kernels; only summation order differs from ATen           (measured <= 1.3e-7)
-  tf32  3e-4   tcgen05 kind::tf32; north_star's bound for this mode is 1e-3        (measured <= 9.8e-5)
+  tf32  1.8e-4 10-bit-mantissa operands (fp16 hi planes, tcgen05 kind::f16), fp32 accumulate, hi + lo residual stream;
+               north_star's bound for this mode is 1e-3                             (measured <= 5.9e-5)
   fp16  2.5e-4 fp16 operands and stored activations, fp32 accumulate; bound 1e-3   (measured <= 7.6e-5)
   bf16  1.8e-3 bf16 operands + bf16 stored activations (log-mel L1 reported by bench) (measured <= 6.2e-4)
 The largest values come from the small custom geometry, whose signal peak (0.16) is 2-5x the others.
@@ -26,7 +27,7 @@ pytestmark = pytest.mark.gpu
 
 MODES = ["fp32", "tf32", "fp16", "bf16"]
 TC_MODES = ["tf32", "fp16", "bf16"]
-TOL = {"fp32": 5e-7, "tf32": 3e-4, "fp16": 2.5e-4, "bf16": 1.8e-3}
+TOL = {"fp32": 5e-7, "tf32": 1.8e-4, "fp16": 2.5e-4, "bf16": 1.8e-3}
 NORTH_STAR_BOUND = 1e-3            # fp32 / tf32 / fp16 modes must stay below this whatever TOL says
 
 
@@ -86,8 +87,8 @@ def test_saturated_tanh(manifest, mode, record):
     record("default_saturated_b1_t16", mode, err, float(np.abs(g["wav"]).max()))
     assert np.abs(wav).max() <= 1.0
     # signal peak 1.0 here (15-25x the other cases, pre-tanh values O(1)): bounds are 3x the values measured
-    # on B200 (fp32 6.5e-6, tf32 7.2e-3, fp16 4.7e-3, bf16 3.7e-2; profiles/r2_parity.md)
-    assert err <= {"fp32": 2e-5, "tf32": 2.2e-2, "fp16": 1.5e-2, "bf16": 1.1e-1}[mode]
+    # on B200 (fp32 6.5e-6, tf32 4.0e-3, fp16 4.7e-3, bf16 3.7e-2; profiles/r2_parity.md)
+    assert err <= {"fp32": 2e-5, "tf32": 1.3e-2, "fp16": 1.5e-2, "bf16": 1.1e-1}[mode]
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -101,7 +102,8 @@ def test_stage_boundaries(manifest, mode):
     run(make_gen(cfg, sd, mode), mel, stages=stages)
     stride = manifest["stage_stride"]
     assert len(stages) == 2 * len(cfg["upsample_rates"]) + 1
-    rtol = {"fp32": 1e-5, "tf32": 4e-3, "fp16": 6e-3, "bf16": 3e-2}[mode]
+    # relative to the stage's peak; tf32: the hooks read the hi halves of the planes (fp16 rounding, measured <= 4.5e-4)
+    rtol = {"fp32": 1e-5, "tf32": 1.5e-3, "fp16": 6e-3, "bf16": 3e-2}[mode]
     for i, s in enumerate(stages):
         s = s.cpu().numpy()
         ref = g[f"stage{i}"]
