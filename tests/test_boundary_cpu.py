@@ -23,7 +23,7 @@ def _built():
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "hfg.h")).read()
-    declared = set(re.findall(r"\b(hfg_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(hfg_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_capi.SYMBOLS)
     lib = ctypes.CDLL(_capi.lib_path())
     for name in declared:
