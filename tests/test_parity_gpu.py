@@ -429,6 +429,39 @@ def test_long_form_against_oracle():
         assert err <= TOL[mode]
 
 
+@pytest.mark.parametrize("geom", [
+    # one resblock of one pair: no ping-pong planes, no MRF sum; the MRF output is the pair's own result
+    dict(upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=64,
+         resblock_kernel_sizes=[3], resblock_dilation_sizes=[[1]]),
+    # resblocks of different depth (1 and 4 pairs): finished outputs in fp32 planes, hi + lo ping-pong only where needed
+    dict(upsample_rates=[2, 2, 2], upsample_kernel_sizes=[4, 4, 4], upsample_initial_channel=128,
+         resblock_kernel_sizes=[5, 3], resblock_dilation_sizes=[[2], [1, 2, 3, 1]]),
+    # four resblocks (three fp32 planes feed the MRF sum) with even dilations
+    dict(upsample_rates=[8], upsample_kernel_sizes=[16], upsample_initial_channel=64,
+         resblock_kernel_sizes=[3, 3, 5, 7], resblock_dilation_sizes=[[1, 2], [4, 1], [1, 1], [2, 2]]),
+])
+@pytest.mark.parametrize("mode", ["tf32", "fp16"])
+def test_unusual_resblock_structures_against_oracle(geom, mode):
+    """The tf32 mode's split plan (fp16 hi + lo planes, fp32 planes for the finished resblock outputs) allocates planes
+    by the structure of the MRF: every branch of that plan against the oracle, next to the fp16 mode on the same input.
+    The workspace is poisoned first."""
+    import oracle
+    cfg = dict(n_mels=32, **geom)
+    sd = synth.make_weights(cfg, 91)
+    mel = synth.make_mel(92, 2, 32, 37)
+    ref = oracle.forward_torch(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    gen = make_gen(cfg, sd, mode)
+    run(gen, mel)
+    if mode == "tf32":
+        assert gen._handle_for(torch.device("cuda", 0)).tf32_plan_is_split()
+    for ws in gen._workspaces.values():
+        ws.fill_(0xFF)                                                 # NaN patterns in every plane and pad row
+    wav = run(gen, mel)
+    err = float(np.abs(wav - ref).max())
+    print(f"structure {geom['resblock_dilation_sizes']}[{mode}]: max-abs {err:.3e} (peak {np.abs(ref).max():.3f})")
+    assert gen.mode == mode and err <= TOL[mode] * max(1.0, float(np.abs(ref).max()) / 0.07)
+
+
 def test_geometry_outside_umma_shapes_falls_back_to_fp32_kernels():
     """Channel counts that are not multiples of 16 (40 -> 20 -> 10) cannot use the UMMA tiles; the
     module must stay on the GPU (fp32 kernels), warn, and still match the oracle."""

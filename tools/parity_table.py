@@ -13,9 +13,9 @@ for r in rows:
     d[r["case"]][r["mode"]] = (max(r["max_abs"], prev[0] if prev else 0.0), r["ref_peak"])
 out = ["# Round 2 — measured parity (B200, final `pytest -m gpu` run of the round; written by the tests into gpurun_out/parity_r2.jsonl)\n",
        "Max-abs error of the waveform (of `mel_pred` for the decoder rows) against the committed golden vectors of the live reference, or",
-       "against the oracle on the same inputs.  `peak` is the peak of the reference signal.  The test tolerances",
+       "against the oracle on the same inputs.  `peak` is the peak of the reference signal (`tf32_fp32_planes_3x97`: the fp32-plane kind::tf32 path of the tf32 mode, forced through the tuning library).  The test tolerances",
        "(`tests/test_parity_gpu.py: TOL`; `tests/test_ar_decoder.py: TOL_MEL`) are about 3x the column maxima.\n",
-       "| case | fp32 | tf32 (fp16 intermediate) | fp16 | bf16 | peak |", "|---|---|---|---|---|---|"]
+       "| case | fp32 | tf32 (split plan: fp16 operand planes, hi + lo residual stream) | fp16 | bf16 | peak |", "|---|---|---|---|---|---|"]
 mx = defaultdict(float)
 for c, v in d.items():
     cells = []
@@ -31,7 +31,7 @@ out.append("| **max over waveform cases (saturated case apart)** | " + " | ".joi
 out += ["",
         "Bounds: north_star demands <= 1e-3 for the fp32/TF32 mode -- met by fp32, tf32 and fp16 with a factor of about 10 or more on every case but the",
         "saturated one (weights x2.25, signal peak 1.0, a quarter of the samples beyond |0.9|: tanh no longer attenuates the rounding of O(1) pre-activations;",
-        "its bounds are 2e-5 / 2.2e-2 / 1.5e-2 / 1.1e-1).  The decoder rows (`ar_decoder_b8`, `config5_b64_mel_pred`) compare the KV-cached CUDA decoder with the",
+        "its bounds are 2e-5 / 1.3e-2 / 1.5e-2 / 1.1e-1).  The decoder rows (`ar_decoder_b8`, `config5_b64_mel_pred`) compare the KV-cached CUDA decoder with the",
         "unmodified reference's O(T^2) loop, frame for frame (signal peak 4.3-4.5).  Other pinned figures: on-device log-mel vs the float64 oracle 7.0e-7 max-abs,",
         "its L1 vs the value the reference's `VocoderLoss.mel_reconstruction_loss` returned 2.0e-7 relative; length regulator and duration rounding bit-exact."]
 print("\n".join(out))
