@@ -272,7 +272,8 @@ def test_kernel_variants_are_bit_identical(mode):
                dict(T, HFG_TC_STREAMS="1"), dict(T, HFG_TC_PAIR_CTAS="1"),
                dict(T, HFG_TC_PAIR_MT="2", HFG_TC_PAIR_OCC2="0"),
                dict(T, HFG_TC_PAIR_GROUPS="2"),                 # every tile as two independently pipelined halves
-               dict(T, HFG_TC_UP_CONTIG="1")]                   # contiguous item blocks in the persistent conv kernel
+               dict(T, HFG_TC_UP_CONTIG="1"),                   # contiguous item blocks in the persistent conv kernel
+               dict(T, HFG_TC_PAIR_EW="12")]                    # three epilogue warps per TMEM lane quarter (one-CTA-per-SM variants)
     group_b = [dict(T, HFG_TC_S2D="0"), dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1"),
                dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_PAIR_MT="1")]
     # group C: the space-to-depth form forced onto every layer that can take it (C = 64 too, all k)

@@ -30,8 +30,9 @@
 
 namespace hfg {
 
-constexpr int kPairEpiWarps = 8;
-constexpr int kPairThreads = 64 + 32 * kPairEpiWarps;
+constexpr int kPairEpiWarps = 8;                  // default; the one-CTA-per-SM variants can run 12 (template parameter EW)
+constexpr int pair_threads(int ew) { return 64 + 32 * ew; }
+constexpr int kPairThreads = pair_threads(kPairEpiWarps);
 constexpr int kPairMaxSA = 6;                     // activation ring slots (K blocks, possibly of several tiles ahead)
 
 struct TcPairArgs {
@@ -131,9 +132,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // LO = true (P = P2 = PREC_FP16): operands are the fp16 hi planes, the residual stream is the pair hi + lo -- the
 // arithmetic of the tf32 mode (10-bit-mantissa operands, fp32 accumulate, >= 22-bit residual stream) at the fp16
 // mode's MMA rate and shared-memory operand bytes, with the fp32 planes' HBM bytes.
-template <int P, int P2, int MINB, int CTAS, bool LO = false>
-__global__ void __launch_bounds__(kPairThreads, MINB)
+// EW = epilogue warps (8 or 12): EW / 4 warps share each TMEM lane quarter.  With three, the (sub-tile, 32-column
+// group) units of an accumulator go round-robin to the warps of a quarter -- the same map in pre2 and epi2, so a
+// warp only ever writes accumulator columns it has itself drained.
+template <int P, int P2, int MINB, int CTAS, bool LO = false, int EW = kPairEpiWarps>
+__global__ void __launch_bounds__(pair_threads(EW), MINB)
 tc_pair_kernel(const TcPairArgs a) {
+    static_assert(EW == 8 || EW == 12, "two or three epilogue warps per TMEM lane quarter");
     extern __shared__ __align__(128) uint8_t tc_pair_smem[];
     uint8_t* smem = tc_pair_smem;
     constexpr int CW = Prec<P>::CW, CW2 = Prec<P2>::CW;
@@ -181,14 +186,14 @@ tc_pair_kernel(const TcPairArgs a) {
         // pair mode: the LEADER's full barriers also collect the peer's "my copy of this stage has landed"
         // (one remote arrive), so its MMA warp waits on a single barrier per stage
         const uint32_t full_count = (CTAS == 2 && rank == 0) ? 2u : 1u;
-        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), full_count); mbar_init(A_EMPTY(i), 1 + kPairEpiWarps); }
+        for (int i = 0; i < a.sa; ++i) { mbar_init(A_FULL(i), full_count); mbar_init(A_EMPTY(i), 1 + EW); }
         for (int i = 0; i < a.sw; ++i) { mbar_init(W_FULL(i), full_count); mbar_init(W_EMPTY(i), 1); }
         mbar_init(ACC1_FULL, 1);
-        mbar_init(H_READY, (kPairEpiWarps / GR) * CTAS);
+        mbar_init(H_READY, (EW / GR) * CTAS);
         mbar_init(ACC2_FULL, 1);
         mbar_init(LO_FULL, 1);
         mbar_init(ACC1_FULL_B, 1);
-        mbar_init(H_READY_B, (kPairEpiWarps / GR) * CTAS);
+        mbar_init(H_READY_B, (EW / GR) * CTAS);
         mbar_init(ACC2_FULL_B, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,7 +209,7 @@ tc_pair_kernel(const TcPairArgs a) {
         }
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < N; i += 32 * kPairEpiWarps) { sB1[i] = a.b1[i]; sB2[i] = a.b2[i]; }
+        for (int i = threadIdx.x - 64; i < N; i += 32 * EW) { sB1[i] = a.b1[i]; sB2[i] = a.b2[i]; }
     }
     tc_fence_before();
     __syncthreads();
@@ -452,13 +457,18 @@ tc_pair_kernel(const TcPairArgs a) {
         // MT2 sub-tiles of N2 columns (MT / 2 and 2 N in space-to-depth form): each accumulator has its own split,
         // and every phase that touches acc2 (pre2, epi2) uses the same one
         // With the tile run as two halves (GR == 2) the warps of `half` own ALL sub-tiles and columns of that half.
-        const bool split1 = GR == 1 && MT == 1, split2 = GR == 1 && MT2 == 1;
-        const int mt_first = GR == 2 ? half * MTg : (split1 ? 0 : half), mt_end = GR == 2 ? (half + 1) * MTg : MT;
-        const int mt_step = (GR == 2 || split1) ? 1 : 2;
+        // Three warps per quarter (EW == 12, GR == 1): every warp walks all sub-tiles and 32-column groups and keeps the
+        // units u = sub-tile * groups + group with u % 3 == its index (`own1` / `own2` below).
+        constexpr bool W3 = EW == 12;
+        const bool split1 = !W3 && GR == 1 && MT == 1, split2 = !W3 && GR == 1 && MT2 == 1;
+        const int mt_first = W3 ? 0 : (GR == 2 ? half * MTg : (split1 ? 0 : half)), mt_end = (!W3 && GR == 2) ? (half + 1) * MTg : MT;
+        const int mt_step = (W3 || GR == 2 || split1) ? 1 : 2;
         const int cs = split1 ? 2 : 1, ch = split1 ? half : 0;           // acc1: 32-column-step stride / phase
-        const int mt2_first = GR == 2 ? half * MT2g : (split2 ? 0 : half), mt2_end = GR == 2 ? (half + 1) * MT2g : MT2;
-        const int mt2_step = (GR == 2 || split2) ? 1 : 2;
+        const int mt2_first = W3 ? 0 : (GR == 2 ? half * MT2g : (split2 ? 0 : half)), mt2_end = (!W3 && GR == 2) ? (half + 1) * MT2g : MT2;
+        const int mt2_step = (W3 || GR == 2 || split2) ? 1 : 2;
         const int cs2 = split2 ? 2 : 1, ch2 = split2 ? half : 0;         // acc2
+        auto own1 = [&](int mt, int col) { return !W3 || (mt * (N >> 5) + (col >> 5)) % 3 == half; };     // acc1 columns
+        auto own2 = [&](int mt, int col) { return !W3 || (mt * (N2 >> 5) + (col >> 5)) % 3 == half; };   // acc2 columns
         const bool upper = GR == 2 && half == 1;                         // this warp's half uses the second barrier set
         const uint32_t acc1_full = upper ? ACC1_FULL_B : ACC1_FULL, h_ready = upper ? H_READY_B : H_READY;
         const uint32_t acc2_full = upper ? ACC2_FULL_B : ACC2_FULL;
@@ -501,6 +511,7 @@ tc_pair_kernel(const TcPairArgs a) {
                         // warps of a lane quarter): this warp's tcgen05.st for tile i+1 may only touch columns
                         // whose tile-i values it has itself already read in epi2
                         if (split2 && (((pp * N + col) >> 5) & 1) != half) continue;
+                        if (!own2(mt, pp * N + col)) continue;
                         float v[16];
                         if constexpr (LO)
                             load_split16(rp + (long long)(c16 / CW) * a_plane, a_plane,
@@ -534,7 +545,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 if (++sa_i == a.sa) { sa_i = 0; sa_ph ^= 1; }
             }
             // LO kernels: every epilogue warp has read its lo cells before any of them overwrites the buffer with H
-            if constexpr (LO) asm volatile("bar.sync 1, %0;" ::"n"(32 * kPairEpiWarps) : "memory");
+            if constexpr (LO) asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
             // ---------- epi1: acc1 -> leaky_relu(. + b1) -> H tile in smem ----------
             if (e == 0) HFG_TL(6, it);
             mbar_wait_sleep(acc1_full, it & 1, (uint32_t)a.epi_sleep_ns);
@@ -551,6 +562,7 @@ tc_pair_kernel(const TcPairArgs a) {
                 uint8_t* hp = a.s2d ? sH + (size_t)(hr >> 1) * 16 + (size_t)(hr & 1) * (N / CW2) * h_plane : sH + (size_t)hr * 16;
                 const uint32_t tbase = acc1 + lane_sel + (uint32_t)(mt * N);
                 for (int c0 = 32 * ch; c0 < N; c0 += 32 * cs) {
+                    if (!own1(mt, c0)) continue;
                     uint32_t r0[16], r1[16];
                     const bool two = c0 + 16 < N;
                     tmem_ld16(tbase + (uint32_t)c0, r0);
@@ -590,7 +602,7 @@ tc_pair_kernel(const TcPairArgs a) {
             // of two 16-byte stores with a 32-byte lane stride
             // (compiled only into the single-CTA 2-byte variants, the ones the space-to-depth rule selects: the CTA-pair
             // and tf32 variants run at their register cap and would pay for the extra path with spills)
-            const bool rows2 = CTAS == 1 && P != PREC_TF32 && a.s2d && !split2 && !acc_store_mode;
+            const bool rows2 = CTAS == 1 && P != PREC_TF32 && !W3 && a.s2d && !split2 && !acc_store_mode;
             if constexpr (CTAS == 1 && P != PREC_TF32)
             for (int mt = mt2_first; mt < mt2_end && !HFG_DBG(a, 8) && rows2; mt += mt2_step) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
@@ -637,6 +649,7 @@ tc_pair_kernel(const TcPairArgs a) {
             for (int mt = mt2_first; mt < mt2_end && !HFG_DBG(a, 8) && !rows2; mt += mt2_step) {
                 const uint32_t tbase = acc2 + lane_sel + (uint32_t)(mt * N2);
                 for (int c0 = 32 * ch2; c0 < N2; c0 += 32 * cs2) {
+                    if (!own2(mt, c0)) continue;
                     const int pp = c0 >= N ? 1 : 0, cb = c0 - pp * N;   // time step of this GEMM row, channel base (N % 32 == 0 when PP = 2)
                     const int lr = (mt * 128 + row) * PP + pp;
                     const int t = t0 + lr;

@@ -653,7 +653,17 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.w_half_stride = L.c1.tc.half_stride[P][vk];
     a.w2_half_stride = g.s2d ? L.c2.tc.s2d_half_stride[P2] : L.c2.tc.half_stride[P2][vk];
     a.s2d = g.s2d; a.k2 = g.k2; a.tap_group2 = g.G2; a.w_stage_bytes = (unsigned)g.stage;
-    a.groups = g.groups;
+    // Twelve epilogue warps (three per TMEM lane quarter) for the variants that own their SM (MINB = 1).  Measured
+    // (profiles/r2_tuning.md section 14): bit-identical and SLOWER (C = 128 k = 3: 50.9 -> 59.6 us) -- the epilogue
+    // chain is not bound by per-warp latency but shares the shared-memory bandwidth with the MMAs' operand reads.
+    // The variants are instantiated in the tuning build only.
+    const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
+#ifdef HFG_TUNING
+    const bool ew12 = !two && env_int("HFG_TC_PAIR_EW", 8) == 12;
+#else
+    constexpr bool ew12 = false;
+#endif
+    a.groups = ew12 ? 1 : g.groups;
     a.kbc = g.kbc;
     a.poll_ns = env_int("HFG_TC_POLL_NS", 40);
     a.epi_sleep_ns = env_int("HFG_TC_EPI_SLEEP_NS", 0);
@@ -677,12 +687,15 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
     a.slope = 0.1f;
     a.timeline = h->pair_timeline;
     // persistent grid: as many CTAs as are co-resident (registers, smem, TMEM columns)
-    const bool two = g.occ >= 2 && env_int("HFG_TC_PAIR_MINB", 2) >= 2;
     const int ctas = g.ctas;
     using KernelFn = void (*)(TcPairArgs);
     KernelFn fn = nullptr;
     if constexpr (LO) {
         static_assert(P == PREC_FP16, "the hi + lo variant runs on fp16 operand planes");
+#ifdef HFG_TUNING
+        if (ew12) fn = ctas == 2 ? tc_pair_kernel<P, P, 1, 2, true, 12> : tc_pair_kernel<P, P, 1, 1, true, 12>;
+        else
+#endif
         if (ctas == 2) fn = two ? tc_pair_kernel<P, P, 2, 2, true> : tc_pair_kernel<P, P, 1, 2, true>;
         else fn = two ? tc_pair_kernel<P, P, 2, 1, true> : tc_pair_kernel<P, P, 1, 1, true>;
     } else if (P == PREC_TF32 && P2 == PREC_FP16) {
@@ -693,13 +706,20 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
         else fn = two ? tc_pair_kernel<P, P, 2, 1> : tc_pair_kernel<P, P, 1, 1>;
     }
     // co-residency: smem / TMEM columns (g.occ) and registers (64 K per SM, allocated per warp in units of 8)
-    int& regs = h->pair_regs[LO ? 4 : (P == PREC_TF32 && P2 == PREC_FP16 ? 3 : P)][two ? 1 : 0][ctas - 1];
+    const bool ew12_used = ew12 && (LO || P != PREC_TF32);
+    const int threads = pair_threads(ew12_used ? 12 : kPairEpiWarps);
+#ifdef HFG_TUNING
+    if constexpr (!LO && P != PREC_TF32) {
+        if (ew12) fn = ctas == 2 ? tc_pair_kernel<P, P, 1, 2, false, 12> : tc_pair_kernel<P, P, 1, 1, false, 12>;
+    }
+#endif
+    int& regs = h->pair_regs[LO ? 4 : (P == PREC_TF32 && P2 == PREC_FP16 ? 3 : P)][ew12_used ? 2 : (two ? 1 : 0)][ctas - 1];
     if (regs == 0) {
         cudaFuncAttributes fa{};
         check_cuda(cudaFuncGetAttributes(&fa, fn), "cudaFuncGetAttributes");
         regs = std::max(1, fa.numRegs);
     }
-    const int occ_regs = 65536 / (((regs + 7) / 8 * 8) * kPairThreads);
+    const int occ_regs = 65536 / (((regs + 7) / 8 * 8) * threads);
     const int occ = std::max(1, std::min(occ_regs, g.occ));
     const int n_sched = (a.n_tiles + ctas - 1) / ctas;
     const int grid = ctas * std::min(n_sched, (h->sm_count / ctas) * occ);
@@ -711,12 +731,12 @@ static void tc_launch_pair(hfg_handle* h, cudaStream_t st, const PairLayers& L, 
                              : (double)B * T * C * ESZ * ((out ? 2 : 1) + n_sum) +
                                (acc ? 4.0 * B * T * C * (acc_mode == TC_ACC_ADD ? 2 : 1) : 0.0) + 2.0 * ESZ * C * C * a.k;
     if (env_int("HFG_TC_VERBOSE", 0))
-        fprintf(stderr, "[pair] gr=%d lo=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
-                g.groups, (int)LO, a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
+        fprintf(stderr, "[pair] ew=%d gr=%d lo=%d N=%d k=%d d=%d MT=%d G=%d sa=%d sw=%d kbc=%d ctas=%d smem=%zu occ=%d minb=%d grid=%d tiles=%d s2d=%d k2=%d G2=%d stage=%zu RH=%d\n",
+                ew12_used ? 12 : 8, a.groups, (int)LO, a.N, a.k, a.dil, g.MT, g.G, g.sa, g.sw, g.kbc, ctas, g.smem, occ, two ? 2 : 1, grid, a.n_tiles, g.s2d, g.k2, g.G2, g.stage, g.RH);
     h->prof_begin(st, label, flops, bytes);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kPairThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = g.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -1127,6 +1147,12 @@ inline void configure_kernels(hfg_handle*) {
     };
     big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 1>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 1>);
     big(tc_pair_kernel<PREC_TF32, PREC_FP16, 1, 2>); big(tc_pair_kernel<PREC_TF32, PREC_FP16, 2, 2>);
+#ifdef HFG_TUNING
+    // twelve epilogue warps (2-byte modes and the split plan, one CTA per SM): tuning build only
+    big(tc_pair_kernel<PREC_BF16, PREC_BF16, 1, 1, false, 12>); big(tc_pair_kernel<PREC_BF16, PREC_BF16, 1, 2, false, 12>);
+    big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 1, false, 12>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 2, false, 12>);
+    big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 1, true, 12>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 2, true, 12>);
+#endif
     // hi + lo variants (split plan of the tf32 mode)
     big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 1, true>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 2, 1, true>);
     big(tc_pair_kernel<PREC_FP16, PREC_FP16, 1, 2, true>); big(tc_pair_kernel<PREC_FP16, PREC_FP16, 2, 2, true>);
