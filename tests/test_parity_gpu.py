@@ -329,6 +329,9 @@ def test_c_abi_error_codes():
     with pytest.raises(_capi.HfgError) as e:           # nothing loaded yet
         h.commit()
     assert e.value.code == _capi.ERR_STATE and "conv_pre.weight" in str(e.value)
+    with pytest.raises(_capi.HfgError) as e:           # the plan of the tf32 mode depends on the committed layers
+        h.tf32_plan_is_split()
+    assert e.value.code == _capi.ERR_STATE
     sd = synth.make_weights(synth.DEFAULT_CONFIG, 1)
     bad = np.zeros((3, 3, 3), np.float32)
     h.set_weight("conv_pre.weight", bad.ctypes.data, bad.shape)

@@ -115,6 +115,7 @@ static void commit(hfg_handle* h) {
     h->free_device_weights();
     h->ups.clear();
     h->mrfs.clear();
+    h->tf32_split = -1;
 
     // conv_pre: Conv1d(n_mels, c0, 7, padding=3)   (reference models/hifigan.py:177-183)
     h->pre = ConvLayer{};

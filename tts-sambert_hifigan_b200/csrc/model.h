@@ -81,6 +81,7 @@ struct hfg_handle {
     int64_t launches = 0;
     int mel_layout = 0;       // 0 = [B, n_mels, T] (reference), 1 = [B, T, n_mels] (acoustic-model output)
     unsigned long long* pair_timeline = nullptr;   // tuning only: phase stamps of the fused pair kernel (hfg_bench_layer)
+    int tf32_split = -1;      // HFG_MODE_TF32 on fp16 hi + lo planes (tc_path.cuh: tc_tf32_mixed): -1 = not evaluated yet
     int pair_regs[5][3][2] = {};                   // registers per thread of tc_pair_kernel<P, P2, MINB, CTAS> (index 3: tf32 with an fp16 intermediate, 4: fp16 operands with fp32 twin planes), filled lazily
 
     std::map<std::string, hfg::HostTensor> sd;   // raw state_dict as set by the caller

@@ -261,7 +261,7 @@ static inline bool tc_stage_sum_planes(const hfg_handle* h, size_t i, int n_chun
 // Planes that only feed MMAs (mel, conv_pre output, an MRF output followed by an upsampler) have no lo twin; the
 // finished resblock outputs that only feed the MRF sum, and the last MRF output (conv_post), are plain fp32 planes.
 // Used when every pair of the configuration fits the fused kernel (else the fp32-plane kind::tf32 path).
-static inline bool tc_tf32_mixed(const hfg_handle* h) {
+static inline bool tc_tf32_mixed_eval(const hfg_handle* h) {
     if (!env_int("HFG_TC_TF32_MIXED", 1)) return false;
     if (h->post_cin % 8 != 0) return false;
     for (size_t i = 0; i < h->ups.size(); ++i) {
@@ -273,6 +273,12 @@ static inline bool tc_tf32_mixed(const hfg_handle* h) {
         if (h->mrfs[i].size() > 1 && !tc_stage_sum_planes(h, i, C / 8, PREC_FP16)) return false;
     }
     return true;
+}
+
+// evaluated once per committed weight set (hfg_handle::tf32_split, reset by commit): every forward asks
+static inline bool tc_tf32_mixed(const hfg_handle* h) {
+    if (h->tf32_split < 0) const_cast<hfg_handle*>(h)->tf32_split = tc_tf32_mixed_eval(h) ? 1 : 0;
+    return h->tf32_split == 1;
 }
 
 struct TcPlan {
