@@ -52,6 +52,22 @@ def test_c_oracle_matches_reference_golden(manifest, name):
             assert err <= 1e-5 * max(1.0, np.abs(ref).max()), (i, err)
 
 
+@pytest.mark.parametrize("name", ["default_b2_t24", "default_weightnorm_b1_t16", "odd_upsample_b1_t20", "small_custom_b3_t33"])
+def test_split_plan_model_stays_close_to_the_reference(manifest, name):
+    """oracle/split_plan_model.py states, rounding by rounding, the arithmetic of HFG_MODE_TF32 on its split plan (fp16
+    operands, fp32 accumulate, fp16 hi + lo residual stream).  Against the reference's golden output the model must
+    differ (operands ARE rounded) and stay far below the mode's 1e-3 bound: this is the error the CUDA path is
+    entitled to, and tests/test_parity_gpu.py holds the CUDA path to the model itself."""
+    cfg, sd, mel = case_inputs(manifest, name)
+    g = load_golden(name)
+    wav = oracle.forward_split_plan(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    err = float(np.abs(wav - g["wav"]).max())
+    peak = float(np.abs(g["wav"]).max())
+    print(f"{name}: split-plan model vs reference max-abs {err:.3e} (peak {peak:.3f})")
+    assert wav.shape == g["wav"].shape
+    assert 1e-6 < err <= 1e-4 * max(1.0, peak / 0.07)
+
+
 def test_weight_norm_schema_and_fold(manifest):
     cfg, sd, _ = case_inputs(manifest, "default_weightnorm_b1_t16")
     g = load_golden("default_weightnorm_b1_t16")
