@@ -52,8 +52,23 @@ def _acc32(fn, x, w, **kw):
     return fn(x.double(), w.double(), None, **kw).float()
 
 
+def _bf(x: torch.Tensor) -> torch.Tensor:
+    """fp32 -> bf16 (round to nearest even) -> fp32."""
+    return x.bfloat16().float()
+
+
 def forward_split_plan(cfg: dict, sd: Dict[str, torch.Tensor], mel: torch.Tensor) -> torch.Tensor:
     """mel [B, n_mels, T] fp32 -> wav [B, 1, T_out] fp32, rounding as HFG_MODE_TF32 does on its split plan."""
+    return forward_mode_model(cfg, sd, mel, "tf32")
+
+
+def forward_mode_model(cfg: dict, sd: Dict[str, torch.Tensor], mel: torch.Tensor, mode: str) -> torch.Tensor:
+    """The same model for every tensor-core mode.  "tf32": the split plan described above.  "fp16" / "bf16": every plane
+    -- the residual stream, the finished resblock outputs, the MRF outputs -- is stored in the operand dtype (no lo
+    half, no fp32 planes); accumulation, pre-load and scaling as above; conv_post reads the 2-byte plane with fp32 FMAs."""
+    assert mode in ("tf32", "fp16", "bf16")
+    split = mode == "tf32"
+    _h = _bf if mode == "bf16" else globals()["_h"]
     if any(k.endswith("weight_g") for k in sd):
         sd = fold_weight_norm(sd)
     sd = {k: v.float() for k, v in sd.items()}
@@ -71,7 +86,7 @@ def forward_split_plan(cfg: dict, sd: Dict[str, torch.Tensor], mel: torch.Tensor
             + sd[f"ups.{i}.bias"].view(1, -1, 1)
         s = _lrelu(v)
         x_hi = _h(s)
-        x_lo = _h(s - x_hi)                                        # X: hi + lo
+        x_lo = _h(s - x_hi) if split else torch.zeros_like(s)      # X: hi + lo (2-byte modes: hi only)
         finals = []
         closing = None
         for j, (rk, dils) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"])):
@@ -96,13 +111,13 @@ def forward_split_plan(cfg: dict, sd: Dict[str, torch.Tensor], mel: torch.Tensor
                 if closes:
                     closing = s
                 elif last:
-                    finals.append(s)                               # fp32 plane
+                    finals.append(s if split else _h(s))           # fp32 plane (2-byte modes: operand dtype)
                 else:
                     hi = _h(s)
-                    lo = _h(s - hi)
+                    lo = _h(s - hi) if split else torch.zeros_like(s)
         if i + 1 < n_up:
-            a16 = _h(closing)                                      # MRF output feeds an upsampler: fp16 only
+            a16 = _h(closing)                                      # MRF output feeds an upsampler: operand dtype only
         else:
-            y32 = closing                                          # last MRF output: fp32, read by conv_post
+            y32 = closing if split else _h(closing)                # last MRF output: fp32 (2-byte modes: operand dtype), read by conv_post
     y = F.conv1d(y32, sd["conv_post.weight"], sd["conv_post.bias"], padding=3)     # fp32 FMAs on the device
     return torch.tanh(y)

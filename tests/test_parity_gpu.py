@@ -291,28 +291,30 @@ def test_kernel_variants_are_bit_identical(mode):
         assert len(set(hashes)) == 1, list(zip(variants, hashes))
 
 
+@pytest.mark.parametrize("mode", TC_MODES)
 @pytest.mark.parametrize("name", ["default_b2_t24", "default_weightnorm_b1_t16", "odd_upsample_b1_t20", "small_custom_b3_t33",
                                   "default_saturated_b1_t16"])
-def test_tf32_mode_error_is_what_its_arithmetic_model_predicts(manifest, name, record):
+def test_mode_error_is_what_its_arithmetic_model_predicts(manifest, name, mode, record):
     """oracle/split_plan_model.py places every rounding of the tf32 mode's split plan where the kernels place it (fp16
     operands and intermediate, fp32 accumulate, hi + lo residual stream, fp32 MRF-sum planes).  Two realisations of
     the same rounding scheme do not agree bit for bit -- a different fp32 summation order flips fp16 roundings, and
     the flips are the error -- but they must show the SAME error level against the reference: the CUDA path's
     max-abs and rms error may not exceed the model's by more than rounding statistics allow.  A kernel that dropped
-    the lo halves of the residual stream (= the fp16 mode, 2.6x the error) or rounded anything else would fail."""
+    the lo halves of the residual stream (= the fp16 mode, 2.6x the error) or rounded anything else would fail.
+    The fp16 and bf16 modes are held to their own models (every plane in the operand dtype) in the same way."""
     import oracle
     cfg, sd, mel = case_inputs(manifest, name)
     ref = load_golden(name)["wav"]
-    gen = make_gen(cfg, sd, "tf32")
+    gen = make_gen(cfg, sd, mode)
     wav = run(gen, mel)
     assert gen._handle_for(torch.device("cuda", 0)).tf32_plan_is_split()
-    model = oracle.forward_split_plan(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel)).numpy()
+    model = oracle.forward_mode_model(cfg, {k: torch.from_numpy(v) for k, v in sd.items()}, torch.from_numpy(mel), mode).numpy()
     rms = lambda x: float(np.sqrt(np.mean(np.square(x, dtype=np.float64))))
     e_gpu, e_model, e_between = (float(np.abs(wav - ref).max()), float(np.abs(model - ref).max()), float(np.abs(wav - model).max()))
     r_gpu, r_model = rms(wav - ref), rms(model - ref)
-    print(f"{name}[tf32]: max-abs vs reference: CUDA {e_gpu:.3e}, model {e_model:.3e}; CUDA vs model {e_between:.3e}; "
+    print(f"{name}[{mode}]: max-abs vs reference: CUDA {e_gpu:.3e}, model {e_model:.3e}; CUDA vs model {e_between:.3e}; "
           f"rms vs reference: CUDA {r_gpu:.3e}, model {r_model:.3e}")
-    record(name + "_split_plan_model_vs_reference", "tf32", e_model, float(np.abs(ref).max()))
+    record(name + "_arithmetic_model_vs_reference", mode, e_model, float(np.abs(ref).max()))
     assert e_gpu <= 2.0 * e_model and e_between <= 2.0 * e_model
     assert r_gpu <= 1.2 * r_model              # measured on B200: 0.97 ... 1.03 on every case
 
