@@ -34,7 +34,7 @@ extern "C" {
 #endif
 
 #define HFG_MAX_STAGES 8
-#define HFG_ABI_VERSION 2
+#define HFG_ABI_VERSION 3   /* 3: + hfg_tf32_plan (additive) */
 
 typedef struct hfg_handle hfg_handle;
 

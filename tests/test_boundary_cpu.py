@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_capi.lib_path())
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.hfg_abi_version() == 2
+    assert lib.hfg_abi_version() == 3
 
 
 def test_config_struct_layout_matches_header():
