@@ -278,16 +278,22 @@ def test_kernel_variants_are_bit_identical(mode):
                dict(T, HFG_TC_S2D="0", HFG_TC_PAIR_MT="1", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_PAIR_MT="1")]
     # group C: the space-to-depth form forced onto every layer that can take it (C = 64 too, all k)
     group_c = [dict(T, HFG_TC_S2D="2"), dict(T, HFG_TC_S2D="2", HFG_TC_PAIR_CTAS="1"), dict(T, HFG_TC_S2D="2", HFG_TC_STREAMS="1")]
-    for variants in (group_a, group_b, group_c):
-        hashes = []
-        for v in variants:
-            env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, **v)
-            out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
-                                 env=env, capture_output=True, text=True, timeout=300)
-            assert out.returncode == 0, out.stderr[-2000:]
-            line = [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
-            hashes.append(line.split()[1])
-            print(v, line)
+    def run_variant(v):
+        env = dict({k: x for k, x in os.environ.items() if not k.startswith("HFG_")}, **v)
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_hash.py"), mode],
+                             env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [l for l in out.stdout.splitlines() if l.startswith("HASH")][0]
+
+    # the variants are independent processes on a small input: four at a time (most of a run is interpreter start-up)
+    from concurrent.futures import ThreadPoolExecutor
+    groups = (group_a, group_b, group_c)
+    with ThreadPoolExecutor(4) as ex:
+        lines = [list(ex.map(run_variant, variants)) for variants in groups]
+    for variants, ls in zip(groups, lines):
+        hashes = [l.split()[1] for l in ls]
+        for v, l in zip(variants, ls):
+            print(v, l)
         assert len(set(hashes)) == 1, list(zip(variants, hashes))
 
 
