@@ -70,3 +70,35 @@ def test_oracles_reproduce_the_live_reference(ref_generator_cls, cfg, batch, fra
     names = [n for n, _ in synth.weight_shapes(cfg)]
     got_c = oracle.forward_c(cfg, plain, names, mel)
     assert got_c.shape == want.shape and np.abs(got_c - want).max() <= TOL, cfg
+
+
+# ---- the KV-cached decoder restatement against the reference's O(T^2) loop ----
+
+@pytest.fixture(scope="module")
+def ref_decoder_cls():
+    sys.path.insert(0, REF)
+    try:
+        from models.ar_decoder import PNCAARDecoder
+    finally:
+        sys.path.remove(REF)
+    return PNCAARDecoder
+
+
+@settings(max_examples=12, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+@given(st.sampled_from([(32, 2), (32, 4), (64, 8), (48, 3)]), st.integers(1, 3), st.sampled_from([32, 96]),
+       st.sampled_from([4, 20]), st.integers(1, 3), st.integers(1, 10), st.integers(0, 999))
+def test_kv_cached_decoder_oracle_reproduces_the_live_reference(ref_decoder_cls, dh, n_layers, d_ff, n_mels, batch, frames, seed):
+    """Random small decoder geometries with the reference's own random initialisation: caching keys / values
+    must not change a single frame (reference models/ar_decoder.py:167-238 recomputes the whole prefix per frame)."""
+    from oracle import ar_decoder as ard_oracle
+    d_model, n_heads = dh
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(seed)
+        ref = ref_decoder_cls(d_model=d_model, n_mels=n_mels, n_layers=n_layers, n_heads=n_heads, d_ff=d_ff).eval()
+        hvar = torch.randn(batch, frames, d_model)
+        with torch.no_grad():
+            want = ref(hvar)
+    with torch.no_grad():
+        got = ard_oracle.decode(ref.state_dict(), hvar, n_layers, n_heads)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max())), (dh, n_layers, d_ff)
