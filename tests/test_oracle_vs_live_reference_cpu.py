@@ -102,3 +102,31 @@ def test_kv_cached_decoder_oracle_reproduces_the_live_reference(ref_decoder_cls,
         got = ard_oracle.decode(ref.state_dict(), hvar, n_layers, n_heads)
     assert got.shape == want.shape
     assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max())), (dh, n_layers, d_ff)
+
+
+# ---- the log-mel restatement against the reference's extract_mel ----
+
+def test_log_mel_oracle_reproduces_the_live_extract_mel():
+    """reference data/audio_processing.py:31-139 with the reference's own configs/config.yaml, on seeded waveforms
+    of several lengths (incl. one shorter than a hop and one that is not a multiple of the hop)."""
+    pytest.importorskip("torchaudio")
+    import yaml
+    from oracle import log_mel as olm
+    sys.path.insert(0, REF)
+    try:
+        from data.audio_processing import extract_mel
+    finally:
+        sys.path.remove(REF)
+    with open(os.path.join(REF, "configs", "config.yaml")) as f:
+        config = yaml.safe_load(f)
+    config.setdefault("debug", {})["print_shapes"] = False
+    a = config["audio"]
+    assert {k: a[k] for k in ("sample_rate", "n_fft", "hop_length", "win_length", "n_mels")} == \
+        {k: olm.AUDIO[k] for k in ("sample_rate", "n_fft", "hop_length", "win_length", "n_mels")}
+    for seed, samples in ((1, 22050), (2, 5000), (3, 700), (4, 256 * 40)):
+        wav = (0.1 * synth.normal(seed, (samples,))).astype(np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = extract_mel(torch.from_numpy(wav), sample_rate=a["sample_rate"], config=config).numpy()
+        got = olm.log_mel(wav[None])[0]
+        assert got.shape == want.shape == (80, samples // 256 + 1)
+        assert np.abs(got - want).max() <= 5e-5, (samples, float(np.abs(got - want).max()))     # fp32 FFT vs float64
