@@ -130,3 +130,26 @@ def test_log_mel_oracle_reproduces_the_live_extract_mel():
         got = olm.log_mel(wav[None])[0]
         assert got.shape == want.shape == (80, samples // 256 + 1)
         assert np.abs(got - want).max() <= 5e-5, (samples, float(np.abs(got - want).max()))     # fp32 FFT vs float64
+
+
+# ---- the length-regulator restatement against the reference module ----
+
+@settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+@given(st.integers(1, 6), st.integers(1, 14), st.integers(1, 9), st.integers(0, 2 ** 31 - 1))
+def test_length_regulator_oracle_reproduces_the_live_module(batch, n_ph, d_model, seed):
+    """reference models/variance_adaptor.py:171-269 on random durations incl. zeros and negatives (clamped to 0 there)."""
+    from oracle import length_regulator as lr_oracle
+    sys.path.insert(0, REF)
+    try:
+        from models.variance_adaptor import LengthRegulator
+    finally:
+        sys.path.remove(REF)
+    rng = np.random.default_rng(seed)
+    henc = rng.standard_normal((batch, n_ph, d_model)).astype(np.float32)
+    dur = rng.integers(-2, 7, size=(batch, n_ph)).astype(np.int64)
+    if dur.clip(0).sum(axis=1).max() == 0:
+        dur[0, 0] = 1                                 # an all-empty batch has no frame axis to compare
+    with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+        want = LengthRegulator()(torch.from_numpy(henc), torch.from_numpy(dur)).numpy()
+    got = lr_oracle.length_regulate(henc, dur)
+    assert got.shape == want.shape and np.array_equal(got, want)
