@@ -69,6 +69,16 @@ CASES = {
 
 
 def run_case(name, spec):
+    out, meta = compute_case(name, spec)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, meta["wav_shape"], "absmax %.4f" % meta["wav_absmax"],
+          "fp32-vs-fp64 %.2e" % meta["fp64_maxdiff"])
+    return meta
+
+
+def compute_case(name, spec):
+    """Run one case on the live reference; returns (arrays of the .npz, manifest entry).  Also used by
+    tests/test_goldens_are_live_cpu.py to re-derive committed vectors."""
     cfg, wseed, mseed, B, T, extra = spec
     cfg = cfg or yaml_cfg()
     gen = HiFiGANGenerator(**cfg).eval()
@@ -109,13 +119,10 @@ def run_case(name, spec):
         for i, s in enumerate(stages):
             out[f"stage{i}"] = s.numpy()[:, :, ::STAGE_STRIDE].copy()
             out[f"stage{i}_shape"] = np.array(s.shape)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     meta = dict(cfg=cfg, weight_seed=wseed, mel_seed=mseed, B=B, T=T, extra=extra,
                 wav_shape=list(wav.shape), wav_absmax=float(wav.abs().max()),
                 fp64_maxdiff=float(out["wav_fp64_maxdiff"]))
-    print(name, meta["wav_shape"], "absmax %.4f" % meta["wav_absmax"],
-          "fp32-vs-fp64 %.2e" % meta["fp64_maxdiff"])
-    return meta
+    return out, meta
 
 
 def wrapper_case():
