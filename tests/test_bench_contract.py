@@ -73,3 +73,20 @@ def test_round2_line_carries_the_baseline_configs():
     assert d["roofline"]["frac"] == pytest.approx(d["roofline"]["achieved"] / d["roofline"]["peak"])
     n8 = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_n8.json")))
     assert n8["n_gpus"] == 8 and n8["config3"]["bf16"]["value"] >= 1e5 and n8["config3"]["bf16"]["e2e"]["value"] >= 1e5
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches both arms the same way; for N > 1 that is torchrun.  Rank 0 alone runs the CPU arm and
+    prints the line, the other rank exits 0 without work (and without a GPU or a process group)."""
+    port = 29500 + os.getpid() % 400
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    _check_common(d)
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["value"] == d["value"] > 0
