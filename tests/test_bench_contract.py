@@ -90,3 +90,12 @@ def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
     _check_common(d)
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["value"] == d["value"] > 0
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="needs a box without a GPU")
+def test_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: the product arm exits non-zero with a clear message instead of timing anything else."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
