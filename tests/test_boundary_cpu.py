@@ -166,3 +166,23 @@ def test_receptive_radius_matches_oracle(cfg):
     assert got == _oracle_radius(cfg)
     if cfg["upsample_rates"] == [8, 8, 2, 2]:
         assert got == 13
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: nothing under the package (Python or CUDA) may import, link or mention it as
+    code, and nothing the GPU box runs may read /root/reference."""
+    import glob
+    import re
+    pkg_dir = os.path.join(ROOT, "tts-sambert_hifigan_b200")
+    srcs = glob.glob(os.path.join(pkg_dir, "**", "*.py"), recursive=True) + glob.glob(os.path.join(pkg_dir, "csrc", "*")) \
+        + [os.path.join(ROOT, "tts_sambert_hifigan_b200.py")] + glob.glob(os.path.join(ROOT, "include", "*.h")) \
+        + glob.glob(os.path.join(ROOT, "examples", "**", "*.c"), recursive=True)
+    assert len(srcs) > 15
+    for p in srcs:
+        text = open(p, encoding="utf-8").read()
+        assert not re.search(r"^\s*(import|from)\s+oracle\b", text, re.M), p
+        assert "hifigan_oracle" not in text and "oracle/_" not in text, p
+        assert "/root/reference" not in text, p
+    # the run-time entry points of the GPU box read no reference file either
+    for p in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(ROOT, p)).read(), p
